@@ -1,0 +1,210 @@
+/*
+ * rhseg_b200 — C-ABI of the B200-native restrictive-hierarchy head / loss / metric path.
+ *
+ * The reference (Banksylel/Restrictive-Hierarchical-Semantic-Segmentation) has no FFI: its
+ * boundary is the Python API of Models/models.py, Metrics/losses.py and
+ * Metrics/performance_metrics.py.  The functions below are what a binding for that path
+ * binds; each one cites the reference lines it replaces (paths relative to the reference
+ * root).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the CALLER owns every buffer (PyTorch allocates them);
+ *   - every entry point is stateless, stream-ordered on `stream` (a cudaStream_t passed as
+ *     void*), never synchronises, never allocates, and is CUDA-graph capturable;
+ *   - tensors are fp32 NCHW.  Feature / logit / probability tensors are contiguous; target
+ *     tensors may be channel slices of a wider tensor, so they carry batch and channel
+ *     strides (in elements) and a contiguous H*W plane;
+ *   - return value: 0 on success, a negative RHSEG_ERR_* for argument errors, or a positive
+ *     cudaError_t from the launch.  Nothing throws.
+ *   - accumulators that cross thread blocks are fp64 (loss statistics, FiLM pool sums,
+ *     weight-gradient sums) or int64 (confusion matrix).
+ */
+#ifndef RHSEG_B200_H
+#define RHSEG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RHSEG_ABI_VERSION 1
+#define RHSEG_MAX_K 16           /* channels per level the table format holds            */
+#define RHSEG_KERNEL_MAX_K 8     /* channels per level the fused kernels are built for    */
+#define RHSEG_TABLE_INTS (4 + 5 * RHSEG_MAX_K)
+#define RHSEG_NSTAT 5            /* per (sample, class) loss statistics, see loss_stats   */
+
+enum {
+  RHSEG_OK = 0,
+  RHSEG_ERR_ARG = -1,         /* null pointer / non-positive size / bad stride           */
+  RHSEG_ERR_UNSUPPORTED = -2, /* K outside [1, RHSEG_KERNEL_MAX_K] etc.                  */
+  RHSEG_ERR_TREE = -3         /* malformed level description                             */
+};
+
+/* activation modes of one level (Models/models.py:269, :282-300) */
+enum {
+  RHSEG_ACT_SIGMOID = 0, /* level 0: P = sigmoid(z)                                      */
+  RHSEG_ACT_GROUPED = 1, /* level >0: per-parent softmax, P_c = P_parent * Q_c           */
+  RHSEG_ACT_ZEROS = 2    /* level >0 without any group: probabilities are zeros          */
+};
+
+int rhseg_abi_version(void);
+const char* rhseg_status_string(int status);
+/* SM count / compute capability of the current device (grid sizing, sm_100a check). */
+int rhseg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------
+ * (1) class tree -> index tables.  Replaces build_hierarchy_indices / get_level_classes /
+ * the child_groups construction and the per-forward string lookups
+ * (Models/models.py:38-54, :82-98, :229-238, :293, :789; Metrics/losses.py:168).
+ *
+ * Host function.  `parent_ch[k]` is the channel (in level L-1) of the parent of channel k
+ * of level L, or -1 for every channel of level 0.  Children of one parent must be
+ * contiguous (they are, by construction of the reference's level lists).  Fills `table`
+ * (RHSEG_TABLE_INTS int32, layout below); the caller uploads it to the device once.
+ *   [0] K  [1] G (#groups)  [2] K_prev  [3] activation mode
+ *   [4 + k]                 parent_ch[k]
+ *   [4 + MAX_K + k]         group_of[k]
+ *   [4 + 2*MAX_K + g]       group_start[g]
+ *   [4 + 3*MAX_K + g]       group_len[g]
+ *   [4 + 4*MAX_K + g]       group_parent[g]   (channel in level L-1)
+ * --------------------------------------------------------------------------------------- */
+int rhseg_tree_compile_level(const int32_t* parent_ch, int K, int K_prev, int32_t* table);
+
+/* ---------------------------------------------------------------------------------------
+ * (2) head, forward.  One level = FiLM (Models/models.py:58-77) folded into the 1x1 head
+ * conv (:177-184, :268, :280, :765, :775), optional bilinear align_corners=True upsample
+ * (:766, :776), sigmoid / restrictive per-parent softmax / composition / concat
+ * (:269, :288-302, :767, :784-796).
+ * --------------------------------------------------------------------------------------- */
+
+/* FiLM fold: cond = prev_psum / n_pix; [gamma|beta] = film_w . cond + film_b;
+ * eff_w[b,k,c] = head_w[k,c] * gamma[b,c]; eff_b[b,k] = head_b[k] + sum_c head_w[k,c] beta[b,c].
+ * film_w == NULL (level 0): eff_w[b] = head_w, eff_b[b] = head_b, gamma_beta untouched.
+ *   head_w [K,C], head_b [K], film_w [2C,K_prev], film_b [2C], prev_psum [B,K_prev] fp64,
+ *   gamma_beta [B,2C] out, eff_w [B,K,C] out, eff_b [B,K] out.                            */
+int rhseg_film_fold(const float* head_w, const float* head_b, const float* film_w, const float* film_b,
+                    const double* prev_psum, double n_pix, int B, int C, int K, int K_prev,
+                    float* gamma_beta, float* eff_w, float* eff_b, void* stream);
+
+/* Level forward.  feats [B,C,Hf,Wf]; eff_w/eff_b from rhseg_film_fold; prev_probs
+ * [B,K_prev,H,W] (NULL at level 0); table = device copy of the level table.
+ * (H,W) == (Hf,Wf): conv + activation fused in one pass over the features.
+ * otherwise: conv at (Hf,Wf) into z_lo [B,K,Hf,Wf] (caller workspace), then one hi-res pass
+ * doing upsample + activation.
+ * Outputs: logits [B,K,H,W], probs [B,K,H,W], psum [B,K] fp64 = sum over pixels of probs
+ * (zeroed here; it is the FiLM pool of the next level).                                   */
+int rhseg_head_level_fwd(const float* feats, const float* eff_w, const float* eff_b,
+                         const float* prev_probs, const int32_t* table,
+                         int B, int C, int Hf, int Wf, int H, int W, int K, int K_prev, int act_mode,
+                         float* z_lo, float* logits, float* probs, double* psum, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (2') head, backward (what autograd does for the reference; closed forms in DESIGN.md).
+ * --------------------------------------------------------------------------------------- */
+
+/* Activation backward at output resolution.
+ *   dz_total = dz_in + d(probs path)/dz, where the gradient arriving at the probabilities is
+ *   dP[b,k,n] = g_uniform[b,k] * inv_npix  (FiLM pool of the next level; NULL -> 0)
+ *             + dp_pix[b,k,n] for channels whose bit is set in pix_mask (NULL/0 -> none).
+ * For grouped levels also accumulates dL/dP_parent into dp_prev[b, parent, n] (+=, caller
+ * pre-initialises; NULL -> skipped).  dz_in may be NULL (-> 0).  dz_out must not alias.   */
+int rhseg_head_act_bwd(const float* logits, const float* prev_probs, const int32_t* table,
+                       const float* dz_in, const double* g_uniform, double inv_npix,
+                       const float* dp_pix, uint32_t pix_mask,
+                       int B, int K, int K_prev, int H, int W, int act_mode,
+                       float* dz_out, float* dp_prev, void* stream);
+
+/* Adjoint of the bilinear align_corners=True upsample: dz_hi [B,K,H,W] -> dz_lo [B,K,Hf,Wf]
+ * (deterministic gather form).                                                            */
+int rhseg_upsample_adjoint(const float* dz_hi, int BK, int Hf, int Wf, int H, int W,
+                           float* dz_lo, void* stream);
+
+/* 1x1 conv backward at feature resolution: dfeats[b,c,n] = sum_k eff_w[b,k,c] dz[b,k,n];
+ * S[b,k,c] = sum_n dz[b,k,n] feats[b,c,n]; s[b,k] = sum_n dz[b,k,n]  (fp64, zeroed here).
+ * dfeats may be NULL (features do not require grad).                                      */
+int rhseg_head_conv_bwd(const float* feats, const float* dz, const float* eff_w,
+                        int B, int C, int K, int n_pix,
+                        float* dfeats, double* S, double* s, void* stream);
+
+/* Parameter gradients of one level from S / s (all sums over the batch):
+ *   d_head_w [K,C], d_head_b [K]; and when film_w != NULL: d_film_w [2C,K_prev],
+ *   d_film_b [2C], g_prev [B,K_prev] fp64 = film_w^T [dgamma|dbeta]  (the uniform gradient
+ *   w.r.t. the previous level's pooled probabilities, before the 1/n_pix).
+ * gamma_beta [B,2C] and prev_psum [B,K_prev] are the forward's.                           */
+int rhseg_head_param_grads(const double* S, const double* s, const float* head_w,
+                           const float* film_w, const float* gamma_beta, const double* prev_psum,
+                           double n_pix, int B, int C, int K, int K_prev,
+                           float* d_head_w, float* d_head_b, float* d_film_w, float* d_film_b,
+                           double* g_prev, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (3) hierarchical loss.  Replaces CrossEntropyLoss / SoftDiceLoss (Metrics/losses.py:16-134)
+ * and hierarchical_consistency_loss (:150-177).
+ * --------------------------------------------------------------------------------------- */
+
+/* One pass over (outs, targets): per (sample, class) statistics, fp64 [B,K,RHSEG_NSTAT]:
+ *   [0] sum_m t*lp   [1] |m|   [2] sum_m p*t   [3] sum_m p   [4] sum_m t,   m = (t != -1)
+ * logits_input != 0: lp = log_softmax(outs), p = softmax(outs) over the K channels;
+ * otherwise lp = p = outs (the modules' logits_input=False mode).  Zeroes `stats` first.
+ * targets: element (b,k,n) at targets[b*t_bstride + k*t_cstride + n].                    */
+int rhseg_loss_stats(const float* outs, const float* targets, long t_bstride, long t_cstride,
+                     int B, int K, int n_pix, int logits_input, double* stats, void* stream);
+
+/* Scalars from the statistics (one tiny launch):
+ *   out[0] = CE   (losses.py:95-119: per class -w*S0/cnt, class mean, NaN sample -> 1, batch mean)
+ *   out[1] = Dice (losses.py:23-66: per sample 1-(2I+smooth)/(U+smooth), NaN samples dropped;
+ *            0 when none is left)      out[2] = number of non-NaN dice samples
+ *   out[3] = number of non-NaN CE samples.      weights [K] fp32 (class_weight).
+ * Also writes coef [B,K,3] fp32 = (dCE/dstat0, dDice/dstat2, dDice/dstat3) per (sample, class),
+ * the closed-form backward coefficients rhseg_loss_bwd consumes (zero for dropped samples). */
+int rhseg_loss_finalize(const double* stats, const float* weights, int B, int K, double smooth,
+                        float* out4, float* coef, void* stream);
+
+/* d(g_ce*CE + g_dice*Dice)/d outs -> dz [B,K,n_pix] (written, not accumulated).
+ * g_ce / g_dice are DEVICE scalars (autograd's upstream gradients; NULL -> 0).            */
+int rhseg_loss_bwd(const float* outs, const float* targets, long t_bstride, long t_cstride,
+                   const float* coef, const float* g_ce, const float* g_dice,
+                   int B, int K, int n_pix, int logits_input, float* dz, void* stream);
+
+/* Consistency term of one (level, parent-group set): for each group g of `table`,
+ * sums[g] = sum_{b,n} | sum_{c in g} cur[b,c,n] - prev[b,parent(g),n] |  (fp64, zeroed here).
+ * The caller divides by B*n_pix and averages over all pairs (losses.py:172-177).          */
+int rhseg_consistency_sums(const float* cur, const float* prev, const int32_t* table,
+                           int B, int K, int K_prev, int n_pix, double* sums, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (4) metrics.  Replaces ProcessClasses + the torchmetrics calls of the five wrappers
+ * (Metrics/performance_metrics.py:27-141) and the train-loop prediction glue
+ * (train.py:206-231, predictEval.py:409-422).
+ * --------------------------------------------------------------------------------------- */
+
+/* Confusion matrix of one level, int64 [nc,nc] (row = target class, col = predicted class),
+ * nc = K (child == 0) or K+1 (child != 0: class 0 = "no channel positive", rows with target
+ * class 0 are dropped = torchmetrics ignore_index=0).  argmax = first maximum, NaN wins.
+ * probs / targets both strided like targets above.  Zeroes `conf` first.                  */
+int rhseg_confusion_matrix(const float* probs, long p_bstride, long p_cstride,
+                           const float* targets, long t_bstride, long t_cstride,
+                           int B, int K, int n_pix, int child, int64_t* conf, void* stream);
+
+/* Per-class ratios from a confusion matrix, torchmetrics arithmetic (int64 -> fp32, ratio,
+ * zero denominator -> 0).  out5 [5,nc] fp32 rows: F1/Dice, Jaccard/IoU, Accuracy (= per-class
+ * recall, average=None), Precision, Recall.  (performance_metrics.py:62-66, :82-86, ...)   */
+int rhseg_metric_ratios(const int64_t* conf, int nc, float* out5, void* stream);
+
+/* Train-path prediction (train.py:206-231): onehot = one_hot(argmax(softmax(logits)))
+ * zeroed where target == -1; eval_t = target with -1 -> 0.  Either output may be NULL.
+ * pred_idx (int32 [B,n_pix], argmax index, optional) may be NULL.                         */
+int rhseg_predict_onehot(const float* logits, const float* targets, long t_bstride, long t_cstride,
+                         int B, int K, int n_pix, float* onehot, float* eval_t, int32_t* pred_idx,
+                         void* stream);
+
+/* Fused metrics straight from logits + ternary targets: identical result
+ * to rhseg_predict_onehot followed by rhseg_confusion_matrix, without the one-hot tensors. */
+int rhseg_confusion_from_logits(const float* logits, const float* targets, long t_bstride, long t_cstride,
+                                int B, int K, int n_pix, int child, int64_t* conf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RHSEG_B200_H */

@@ -1,0 +1,205 @@
+// Shared device helpers for the rhseg_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#pragma GCC visibility push(default)
+#include "rhseg_b200.h"
+#pragma GCC visibility pop
+
+#define RHSEG_TBL_PARENT (4)
+#define RHSEG_TBL_GROUP_OF (4 + RHSEG_MAX_K)
+#define RHSEG_TBL_GSTART (4 + 2 * RHSEG_MAX_K)
+#define RHSEG_TBL_GLEN (4 + 3 * RHSEG_MAX_K)
+#define RHSEG_TBL_GPARENT (4 + 4 * RHSEG_MAX_K)
+
+#define RHSEG_LAUNCH_CHECK()                      \
+  do {                                            \
+    cudaError_t e__ = cudaGetLastError();         \
+    if (e__ != cudaSuccess) return (int)e__;      \
+  } while (0)
+
+#define RHSEG_CUDA(call)                          \
+  do {                                            \
+    cudaError_t e__ = (call);                     \
+    if (e__ != cudaSuccess) return (int)e__;      \
+  } while (0)
+
+// K -> template dispatch (K in [1, RHSEG_KERNEL_MAX_K])
+#define RHSEG_DISPATCH_K(K, ...)                                 \
+  switch (K) {                                                   \
+    case 1: { constexpr int KK = 1; __VA_ARGS__; } break;        \
+    case 2: { constexpr int KK = 2; __VA_ARGS__; } break;        \
+    case 3: { constexpr int KK = 3; __VA_ARGS__; } break;        \
+    case 4: { constexpr int KK = 4; __VA_ARGS__; } break;        \
+    case 5: { constexpr int KK = 5; __VA_ARGS__; } break;        \
+    case 6: { constexpr int KK = 6; __VA_ARGS__; } break;        \
+    case 7: { constexpr int KK = 7; __VA_ARGS__; } break;        \
+    case 8: { constexpr int KK = 8; __VA_ARGS__; } break;        \
+    default: return RHSEG_ERR_UNSUPPORTED;                       \
+  }
+
+namespace rhseg {
+
+__host__ __device__ constexpr int pad_k(int K) { return K <= 1 ? 1 : (K <= 2 ? 2 : (K <= 4 ? 4 : 8)); }
+__host__ __device__ constexpr int log2_pow2(int v) { return v <= 1 ? 0 : 1 + log2_pow2(v / 2); }
+
+// ---- streaming global memory access (read-once data: do not allocate in L1) ----
+template <int VEC> struct Vec;
+template <> struct Vec<1> { float v[1]; };
+template <> struct __align__(8) Vec<2> { float v[2]; };
+template <> struct __align__(16) Vec<4> { float v[4]; };
+
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> ld_stream(const float* p) {
+  Vec<VEC> r;
+  if constexpr (VEC == 4) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+  } else if constexpr (VEC == 2) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
+  } else {
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r.v[0]) : "l"(p));
+  }
+  return r;
+}
+
+// cached variant (data that is re-read by neighbouring threads / CTAs: keep it in L1/L2)
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> ld_cached(const float* p) {
+  Vec<VEC> r;
+  if constexpr (VEC == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_stream(float* p, const Vec<VEC>& r) {
+  if constexpr (VEC == 4) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]) : "memory");
+  } else if constexpr (VEC == 2) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(r.v[0]), "f"(r.v[1]) : "memory");
+  } else {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" :: "l"(p), "f"(r.v[0]) : "memory");
+  }
+}
+
+// ---- warp / block reductions ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Reduce NV (power of two, <= 32) per-lane values across the warp with NV-1 + (5-log2 NV)
+// shuffles (recursive halving, then butterfly).  On return every lane holds in v[0] the warp
+// total of value index `transposed_index<NV>(lane)`.
+template <int NV>
+__device__ __forceinline__ void warp_reduce_transposed(float (&v)[NV], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = hi ? v[i + n / 2] : v[i];
+      const float send = hi ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+template <int NV>
+__device__ __forceinline__ int transposed_index(int lane) {
+  // bits of the lane id consumed by the halving steps, most significant first
+  constexpr int L = log2_pow2(NV);
+  return (lane >> (5 - L)) & (NV - 1);
+}
+// lanes for which (lane & low_mask) == 0 are the designated writers (one per value index)
+template <int NV>
+__device__ __forceinline__ bool transposed_writer(int lane) {
+  constexpr int L = log2_pow2(NV);
+  return (lane & ((1 << (5 - L)) - 1)) == 0;
+}
+
+// ---- per-pixel activation math (uniform table fields live in registers) ----
+struct LevelInfo {
+  int start_mask;  // bit k set: channel k is the first channel of its group
+  int parent[RHSEG_KERNEL_MAX_K];
+};
+
+__device__ __forceinline__ float sigmoidf_ref(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+// Segmented (per contiguous group) softmax over K channels; groups start where start_mask has a bit.
+template <int K>
+__device__ __forceinline__ void grouped_softmax(const float (&z)[K], int start_mask, float (&q)[K]) {
+  float m[K];
+  m[0] = z[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) m[k] = ((start_mask >> k) & 1) ? z[k] : fmaxf(m[k - 1], z[k]);
+#pragma unroll
+  for (int k = K - 2; k >= 0; --k) m[k] = ((start_mask >> (k + 1)) & 1) ? m[k] : m[k + 1];
+  float e[K], s[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) e[k] = expf(z[k] - m[k]);
+  s[0] = e[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) s[k] = ((start_mask >> k) & 1) ? e[k] : s[k - 1] + e[k];
+#pragma unroll
+  for (int k = K - 2; k >= 0; --k) s[k] = ((start_mask >> (k + 1)) & 1) ? s[k] : s[k + 1];
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = e[k] / s[k];
+}
+
+// Per-group sum broadcast back to every member: out[k] = sum_{j in group(k)} x[j].
+template <int K>
+__device__ __forceinline__ void group_sum(const float (&x)[K], int start_mask, float (&out)[K]) {
+  out[0] = x[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) out[k] = ((start_mask >> k) & 1) ? x[k] : out[k - 1] + x[k];
+#pragma unroll
+  for (int k = K - 2; k >= 0; --k) out[k] = ((start_mask >> (k + 1)) & 1) ? out[k] : out[k + 1];
+}
+
+// softmax over all K channels, ATen op order (max, sequential sum of expf(z-max), expf/sum)
+template <int K>
+__device__ __forceinline__ void full_softmax(const float (&z)[K], float (&p)[K], float& mx, float& sum) {
+  mx = z[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) mx = fmaxf(mx, z[k]);
+  sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { p[k] = expf(z[k] - mx); sum += p[k]; }
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] = p[k] / sum;
+}
+
+template <int K>
+__device__ __forceinline__ LevelInfo load_level_info(const int32_t* __restrict__ table) {
+  LevelInfo li;
+  li.start_mask = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    li.parent[k] = table ? table[RHSEG_TBL_PARENT + k] : -1;
+    const int g = table ? table[RHSEG_TBL_GROUP_OF + k] : k;
+    const int gs = table ? table[RHSEG_TBL_GSTART + g] : k;
+    if (gs == k) li.start_mask |= (1 << k);
+  }
+  return li;
+}
+
+}  // namespace rhseg

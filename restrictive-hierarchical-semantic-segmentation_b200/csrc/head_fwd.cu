@@ -1,0 +1,466 @@
+// Head forward: FiLM fold, fused 1x1 conv + activation (full-resolution donors, UNet), and the
+// low-resolution conv + fused upsample/activation pass (HRNet).
+// Reference semantics: Models/models.py:58-77 (FiLM), :177-184/:268/:280 (1x1 heads),
+// :269/:288-302 (sigmoid, restrictive softmax, composition, concat), :766/:776 (upsample).
+#include "common.cuh"
+
+namespace rhseg {
+
+// ------------------------------------------------------------------------------------
+// FiLM fold (tiny): one CTA per sample.
+// ------------------------------------------------------------------------------------
+__global__ void film_fold_kernel(const float* __restrict__ head_w, const float* __restrict__ head_b,
+                                 const float* __restrict__ film_w, const float* __restrict__ film_b,
+                                 const double* __restrict__ prev_psum, double n_pix, int C, int K, int K_prev,
+                                 float* __restrict__ gamma_beta, float* __restrict__ eff_w,
+                                 float* __restrict__ eff_b) {
+  extern __shared__ float sm[];  // cond[K_prev] | beta-dot partials[K * nwarps]
+  const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  float* cond = sm;
+  float* part = sm + RHSEG_MAX_K;
+  if (film_w == nullptr) {
+    for (int i = tid; i < K * C; i += nthr) eff_w[(size_t)b * K * C + i] = head_w[i];
+    for (int k = tid; k < K; k += nthr) eff_b[b * K + k] = head_b[k];
+    return;
+  }
+  if (tid < K_prev) cond[tid] = (float)(prev_psum[b * K_prev + tid] / n_pix);  // AdaptiveAvgPool2d(1)
+  __syncthreads();
+  float bdot[RHSEG_KERNEL_MAX_K];
+#pragma unroll
+  for (int k = 0; k < RHSEG_KERNEL_MAX_K; ++k) bdot[k] = 0.f;
+  for (int c = tid; c < C; c += nthr) {
+    float g = film_b[c], be = film_b[C + c];
+    for (int j = 0; j < K_prev; ++j) {  // Linear(K_prev, 2C): same accumulation order as a dot product
+      g = fmaf(film_w[(size_t)c * K_prev + j], cond[j], g);
+      be = fmaf(film_w[(size_t)(C + c) * K_prev + j], cond[j], be);
+    }
+    gamma_beta[(size_t)b * 2 * C + c] = g;
+    gamma_beta[(size_t)b * 2 * C + C + c] = be;
+#pragma unroll
+    for (int k = 0; k < RHSEG_KERNEL_MAX_K; ++k)
+      if (k < K) {
+        const float w = head_w[(size_t)k * C + c];
+        eff_w[((size_t)b * K + k) * C + c] = w * g;
+        bdot[k] = fmaf(w, be, bdot[k]);
+      }
+  }
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+#pragma unroll
+  for (int k = 0; k < RHSEG_KERNEL_MAX_K; ++k) {
+    const float v = warp_sum(bdot[k]);
+    if (lane == 0 && k < K) part[k * nwarp + warp] = v;
+  }
+  __syncthreads();
+  if (tid < K) {
+    float acc = head_b[tid];
+    for (int w = 0; w < nwarp; ++w) acc += part[tid * nwarp + w];
+    eff_b[b * K + tid] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Activation epilogue shared by the fused and the upsampled path.  P pixels per thread.
+// ------------------------------------------------------------------------------------
+template <int K, int P, int MODE>
+__device__ __forceinline__ void activate(const float (&z)[K][P], const float (&pp)[K][P], int start_mask,
+                                         float (&prob)[K][P]) {
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    if constexpr (MODE == RHSEG_ACT_SIGMOID) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) prob[k][p] = sigmoidf_ref(z[k][p]);
+    } else if constexpr (MODE == RHSEG_ACT_GROUPED) {
+      float zz[K], q[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) zz[k] = z[k][p];
+      // softmax(z_g + log(P_p + eps)) == softmax(z_g): the gate is constant inside a group
+      grouped_softmax<K>(zz, start_mask, q);
+#pragma unroll
+      for (int k = 0; k < K; ++k) prob[k][p] = pp[k][p] * q[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) prob[k][p] = 0.f;
+    }
+  }
+}
+
+// per-thread partial sums of the probabilities -> one fp64 atomic per (CTA, channel)
+template <int K, int NWARP>
+__device__ __forceinline__ void block_psum(const float (&ps)[K], double* __restrict__ psum_b, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float v = warp_sum(ps[k]);
+    if (lane == 0) red[warp * K + k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) acc += (double)red[w * K + threadIdx.x];
+    atomicAdd(&psum_b[threadIdx.x], acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Fused 1x1 conv (+ activation).  Each thread owns J vectors of VEC consecutive pixels and
+// walks all C channel planes; the per-sample effective weights sit in shared memory as
+// [C][KP] so that one (vector) broadcast load feeds K*J*VEC FMAs.
+// MODE 3 = conv only (writes `logits` at feature resolution; HRNet low-res pass).
+// ------------------------------------------------------------------------------------
+constexpr int MODE_CONV_ONLY = 3;
+
+template <int K, int VEC, int J, int MODE, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
+head_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ eff_w,
+                const float* __restrict__ eff_b, const float* __restrict__ prev_probs,
+                const int32_t* __restrict__ table, int C, int N, int K_prev,
+                float* __restrict__ logits, float* __restrict__ probs, double* __restrict__ psum) {
+  constexpr int KP = pad_k(K);
+  constexpr int P = J * VEC;
+  extern __shared__ __align__(16) float smem[];
+  float* w_t = smem;                   // [C][KP]
+  float* red = smem + (size_t)C * KP;  // [THREADS/32][K]
+  const int b = blockIdx.y, tid = threadIdx.x;
+
+  {
+    const float* wsrc = eff_w + (size_t)b * K * C;
+    for (int i = tid; i < K * C; i += THREADS) {
+      const int k = i / C, c = i - k * C;
+      w_t[c * KP + k] = wsrc[i];
+    }
+    if constexpr (KP > K)
+      for (int i = tid; i < (KP - K) * C; i += THREADS) {
+        const int k = K + i / C, c = i % C;
+        w_t[c * KP + k] = 0.f;
+      }
+  }
+  __syncthreads();
+
+  const long chunk0 = (long)blockIdx.x * (THREADS * P);
+  long px[J];
+  bool ok[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    px[j] = chunk0 + (long)j * THREADS * VEC + (long)tid * VEC;
+    ok[j] = px[j] < N;  // N % VEC == 0 is guaranteed by the launcher
+  }
+
+  float acc[K][P];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float bk = eff_b[b * K + k];
+#pragma unroll
+    for (int p = 0; p < P; ++p) acc[k][p] = bk;
+  }
+
+  const float* fb = feats + (size_t)b * C * N;
+  int c0 = 0;
+  for (; c0 + UNROLL <= C; c0 += UNROLL) {
+    Vec<VEC> f[UNROLL][J];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        if (ok[j]) f[u][j] = ld_stream<VEC>(fb + (size_t)(c0 + u) * N + px[j]);
+        else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) f[u][j].v[v] = 0.f;
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      float w[KP];
+      if constexpr (KP == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(w_t + (c0 + u) * KP);
+        w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+      } else if constexpr (KP == 8) {
+        const float4 t0 = *reinterpret_cast<const float4*>(w_t + (c0 + u) * KP);
+        const float4 t1 = *reinterpret_cast<const float4*>(w_t + (c0 + u) * KP + 4);
+        w[0] = t0.x; w[1] = t0.y; w[2] = t0.z; w[3] = t0.w; w[4] = t1.x; w[5] = t1.y; w[6] = t1.z; w[7] = t1.w;
+      } else if constexpr (KP == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(w_t + (c0 + u) * KP);
+        w[0] = t.x; w[1] = t.y;
+      } else {
+        w[0] = w_t[c0 + u];
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[k][j * VEC + v] = fmaf(w[k], f[u][j].v[v], acc[k][j * VEC + v]);
+    }
+  }
+  for (; c0 < C; ++c0) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      if (!ok[j]) continue;
+      const Vec<VEC> f = ld_stream<VEC>(fb + (size_t)c0 * N + px[j]);
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[k][j * VEC + v] = fmaf(w_t[c0 * KP + k], f.v[v], acc[k][j * VEC + v]);
+    }
+  }
+
+  float* zb = logits + (size_t)b * K * N;
+  if constexpr (MODE == MODE_CONV_ONLY) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      if (!ok[j]) continue;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        Vec<VEC> o;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) o.v[v] = acc[k][j * VEC + v];
+        *reinterpret_cast<Vec<VEC>*>(zb + (size_t)k * N + px[j]) = o;  // re-read soon: keep cached
+      }
+    }
+    return;
+  } else {
+    const LevelInfo li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? table : nullptr);
+    float pp[K][P];
+    if constexpr (MODE == RHSEG_ACT_GROUPED) {
+      const float* pb = prev_probs + (size_t)b * K_prev * N;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if ((li.start_mask >> k) & 1) {
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            Vec<VEC> t;
+            if (ok[j]) t = ld_cached<VEC>(pb + (size_t)li.parent[k] * N + px[j]);
+            else {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) t.v[v] = 0.f;
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) pp[k][j * VEC + v] = t.v[v];
+          }
+        } else {
+#pragma unroll
+          for (int p = 0; p < P; ++p) pp[k][p] = pp[k > 0 ? k - 1 : 0][p];
+        }
+      }
+    }
+    float prob[K][P];
+    activate<K, P, MODE>(acc, pp, li.start_mask, prob);
+    float ps[K];
+    float* pb_out = probs + (size_t)b * K * N;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      ps[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        if (!ok[j]) continue;
+        Vec<VEC> zo, po;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          zo.v[v] = acc[k][j * VEC + v];
+          po.v[v] = prob[k][j * VEC + v];
+          ps[k] += po.v[v];
+        }
+        *reinterpret_cast<Vec<VEC>*>(zb + (size_t)k * N + px[j]) = zo;
+        *reinterpret_cast<Vec<VEC>*>(pb_out + (size_t)k * N + px[j]) = po;
+      }
+    }
+    block_psum<K, THREADS / 32>(ps, psum + (size_t)b * K, red);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// HRNet hi-res pass: bilinear (align_corners=True) upsample of the low-res logits fused with
+// the activation.  Index/lambda arithmetic follows ATen's upsample_bilinear2d (fp32 scale =
+// (in-1)/(out-1), src = scale*dst, i0 = (int)src, lambda1 = src - i0).
+// ------------------------------------------------------------------------------------
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp make_lerp(int dst, float scale, int in_size) {
+  Lerp r;
+  const float src = scale * (float)dst;
+  r.i0 = (int)src;
+  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.0f - r.l1;
+  return r;
+}
+
+template <int K, int VEC, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+upsample_act_kernel(const float* __restrict__ z_lo, const float* __restrict__ prev_probs,
+                    const int32_t* __restrict__ table, int Hf, int Wf, int H, int W, int K_prev,
+                    float sy, float sx, long total_vec, float* __restrict__ logits,
+                    float* __restrict__ probs, double* __restrict__ psum, int vec_per_sample) {
+  __shared__ float red[(THREADS / 32) * K];
+  const int b = blockIdx.y;
+  const long vi = (long)blockIdx.x * THREADS + threadIdx.x;  // vector index inside the sample
+  const bool ok = vi < vec_per_sample;
+  const int wv = W / VEC;
+  const int y = ok ? (int)(vi / wv) : 0;
+  const int x0 = ok ? (int)(vi - (long)y * wv) * VEC : 0;
+  const long N = (long)H * W, Nf = (long)Hf * Wf;
+  const long px = (long)y * W + x0;
+
+  float z[K][VEC], pp[K][VEC], prob[K][VEC];
+  const LevelInfo li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? table : nullptr);
+  if (ok) {
+    const Lerp ly = make_lerp(y, sy, Hf);
+    Lerp lx[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) lx[v] = make_lerp(x0 + v, sx, Wf);
+    const float* zb = z_lo + (size_t)b * K * Nf;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float* r0 = zb + (size_t)k * Nf + (size_t)ly.i0 * Wf;
+      const float* r1 = zb + (size_t)k * Nf + (size_t)ly.i1 * Wf;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float a = __ldg(r0 + lx[v].i0), bq = __ldg(r0 + lx[v].i1);
+        const float c = __ldg(r1 + lx[v].i0), d = __ldg(r1 + lx[v].i1);
+        z[k][v] = ly.l0 * (lx[v].l0 * a + lx[v].l1 * bq) + ly.l1 * (lx[v].l0 * c + lx[v].l1 * d);
+      }
+    }
+    if constexpr (MODE == RHSEG_ACT_GROUPED) {
+      const float* pb = prev_probs + (size_t)b * K_prev * N;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if ((li.start_mask >> k) & 1) {
+          const Vec<VEC> t = ld_cached<VEC>(pb + (size_t)li.parent[k] * N + px);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) pp[k][v] = t.v[v];
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) pp[k][v] = pp[k > 0 ? k - 1 : 0][v];
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { z[k][v] = 0.f; pp[k][v] = 0.f; }
+  }
+  activate<K, VEC, MODE>(z, pp, li.start_mask, prob);
+  float ps[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    ps[k] = 0.f;
+    if (ok) {
+      Vec<VEC> zo, po;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { zo.v[v] = z[k][v]; po.v[v] = prob[k][v]; ps[k] += po.v[v]; }
+      *reinterpret_cast<Vec<VEC>*>(logits + ((size_t)b * K + k) * N + px) = zo;
+      *reinterpret_cast<Vec<VEC>*>(probs + ((size_t)b * K + k) * N + px) = po;
+    }
+  }
+  block_psum<K, THREADS / 32>(ps, psum + (size_t)b * K, red);
+}
+
+template <int K, int VEC, int J, int MODE, int THREADS, int UNROLL>
+static int launch_fwd(const float* feats, const float* eff_w, const float* eff_b, const float* prev_probs,
+                      const int32_t* table, int B, int C, int N, int K_prev, float* logits, float* probs,
+                      double* psum, cudaStream_t st) {
+  constexpr int KP = pad_k(K);
+  const size_t smem = ((size_t)C * KP + (THREADS / 32) * K) * sizeof(float);
+  auto kern = head_fwd_kernel<K, VEC, J, MODE, THREADS, UNROLL>;
+  if (smem > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long chunk = (long)THREADS * VEC * J;
+  dim3 grid((unsigned)((N + chunk - 1) / chunk), B);
+  kern<<<grid, THREADS, smem, st>>>(feats, eff_w, eff_b, prev_probs, table, C, N, K_prev, logits, probs, psum);
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+template <int K, int MODE>
+static int fwd_fullres(const float* feats, const float* eff_w, const float* eff_b, const float* prev_probs,
+                       const int32_t* table, int B, int C, int N, int K_prev, float* logits, float* probs,
+                       double* psum, cudaStream_t st) {
+  if (N % 4 == 0)
+    return launch_fwd<K, 4, (K <= 4 ? 2 : 1), MODE, 256, (K <= 4 ? 4 : 8)>(feats, eff_w, eff_b, prev_probs, table, B, C,
+                                                                          N, K_prev, logits, probs, psum, st);
+  return launch_fwd<K, 1, (K <= 4 ? 4 : 2), MODE, 128, 8>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev,
+                                                          logits, probs, psum, st);
+}
+
+template <int K, int MODE>
+static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32_t* table, int B, int Hf, int Wf,
+                         int H, int W, int K_prev, float* logits, float* probs, double* psum, cudaStream_t st) {
+  const float sy = H > 1 ? (float)(Hf - 1) / (float)(H - 1) : 0.f;
+  const float sx = W > 1 ? (float)(Wf - 1) / (float)(W - 1) : 0.f;
+  constexpr int THREADS = 256;
+  if (W % 4 == 0) {
+    const int vps = H * (W / 4);
+    dim3 grid((vps + THREADS - 1) / THREADS, B);
+    upsample_act_kernel<K, 4, MODE, THREADS><<<grid, THREADS, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev,
+                                                                       sy, sx, 0, logits, probs, psum, vps);
+  } else {
+    const int vps = H * W;
+    dim3 grid((vps + THREADS - 1) / THREADS, B);
+    upsample_act_kernel<K, 1, MODE, THREADS><<<grid, THREADS, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev,
+                                                                       sy, sx, 0, logits, probs, psum, vps);
+  }
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+}  // namespace rhseg
+
+using namespace rhseg;
+
+extern "C" int rhseg_film_fold(const float* head_w, const float* head_b, const float* film_w, const float* film_b,
+                               const double* prev_psum, double n_pix, int B, int C, int K, int K_prev,
+                               float* gamma_beta, float* eff_w, float* eff_b, void* stream) {
+  if (!head_w || !head_b || !eff_w || !eff_b || B <= 0 || C <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  if (film_w) {
+    if (!film_b || !prev_psum || !gamma_beta || n_pix <= 0) return RHSEG_ERR_ARG;
+    if (K_prev < 1 || K_prev > RHSEG_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  }
+  const int threads = 256;
+  const size_t smem = (RHSEG_MAX_K + RHSEG_KERNEL_MAX_K * (threads / 32)) * sizeof(float);
+  film_fold_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(head_w, head_b, film_w, film_b, prev_psum, n_pix, C, K,
+                                                             K_prev, gamma_beta, eff_w, eff_b);
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+extern "C" int rhseg_head_level_fwd(const float* feats, const float* eff_w, const float* eff_b,
+                                    const float* prev_probs, const int32_t* table, int B, int C, int Hf, int Wf,
+                                    int H, int W, int K, int K_prev, int act_mode, float* z_lo, float* logits,
+                                    float* probs, double* psum, void* stream) {
+  if (!feats || !eff_w || !eff_b || !logits || !probs || !psum) return RHSEG_ERR_ARG;
+  if (B <= 0 || C <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  if (act_mode == RHSEG_ACT_GROUPED && (!prev_probs || !table || K_prev < 1)) return RHSEG_ERR_ARG;
+  if (act_mode < 0 || act_mode > RHSEG_ACT_ZEROS) return RHSEG_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  RHSEG_CUDA(cudaMemsetAsync(psum, 0, sizeof(double) * B * K, st));
+  const bool up = (H != Hf) || (W != Wf);
+  const int Nf = Hf * Wf;
+  if (!up) {
+    RHSEG_DISPATCH_K(K, {
+      if (act_mode == RHSEG_ACT_SIGMOID)
+        return fwd_fullres<KK, RHSEG_ACT_SIGMOID>(feats, eff_w, eff_b, prev_probs, table, B, C, Nf, K_prev, logits, probs, psum, st);
+      if (act_mode == RHSEG_ACT_GROUPED)
+        return fwd_fullres<KK, RHSEG_ACT_GROUPED>(feats, eff_w, eff_b, prev_probs, table, B, C, Nf, K_prev, logits, probs, psum, st);
+      return fwd_fullres<KK, RHSEG_ACT_ZEROS>(feats, eff_w, eff_b, prev_probs, table, B, C, Nf, K_prev, logits, probs, psum, st);
+    });
+  }
+  if (!z_lo) return RHSEG_ERR_ARG;
+  RHSEG_DISPATCH_K(K, {
+    int rc;
+    if (Nf % 4 == 0)
+      rc = launch_fwd<KK, 4, 1, MODE_CONV_ONLY, 128, 8>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
+    else
+      rc = launch_fwd<KK, 1, 1, MODE_CONV_ONLY, 128, 16>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
+    if (rc != RHSEG_OK) return rc;
+    if (act_mode == RHSEG_ACT_SIGMOID)
+      return fwd_upsampled<KK, RHSEG_ACT_SIGMOID>(z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, logits, probs, psum, st);
+    if (act_mode == RHSEG_ACT_GROUPED)
+      return fwd_upsampled<KK, RHSEG_ACT_GROUPED>(z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, logits, probs, psum, st);
+    return fwd_upsampled<KK, RHSEG_ACT_ZEROS>(z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, logits, probs, psum, st);
+  });
+  return RHSEG_OK;
+}

@@ -1,0 +1,361 @@
+// Hierarchical loss: one statistics pass (CE + Dice sums per sample and class), a tiny
+// finalize kernel (scalars + closed-form backward coefficients) and one gradient pass.
+// Reference semantics: Metrics/losses.py:16-134 (SoftDiceLoss, CrossEntropyLoss) and
+// :150-177 (hierarchical_consistency_loss).
+#include <math.h>
+#include "common.cuh"
+
+namespace rhseg {
+
+__device__ __forceinline__ bool vec_ok_ptr(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------------------------------------
+// statistics pass.  grid = (chunks, B); each thread handles ITER vectors of VEC pixels.
+// per (b, c): [0] sum_m t*lp  [1] |m|  [2] sum_m p*t  [3] sum_m p  [4] sum_m t
+// ------------------------------------------------------------------------------------
+template <int K, int VEC, int ITER, int THREADS, bool LOGITS>
+__global__ void __launch_bounds__(THREADS)
+loss_stats_kernel(const float* __restrict__ outs, const float* __restrict__ targets, long t_bstride,
+                  long t_cstride, long N, double* __restrict__ stats) {
+  constexpr int NWARP = THREADS / 32;
+  constexpr int NS = RHSEG_NSTAT;
+  __shared__ float red[NWARP][K * NS];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  float a[K][NS];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < NS; ++j) a[k][j] = 0.f;
+
+  const float* ob = outs + (size_t)b * K * N;
+  const float* tb = targets + (size_t)b * t_bstride;
+  const long chunk0 = (long)blockIdx.x * (THREADS * VEC * ITER);
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const long px = chunk0 + (long)it * THREADS * VEC + (long)tid * VEC;
+    if (px >= N) continue;
+    float z[K][VEC], t[K][VEC];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const Vec<VEC> zv = ld_cached<VEC>(ob + (size_t)k * N + px);
+      const Vec<VEC> tv = ld_cached<VEC>(tb + (size_t)k * t_cstride + px);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { z[k][v] = zv.v[v]; t[k][v] = tv.v[v]; }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float p[K], lp[K];
+      if constexpr (LOGITS) {
+        float zz[K], mx, sum;
+#pragma unroll
+        for (int k = 0; k < K; ++k) zz[k] = z[k][v];
+        full_softmax<K>(zz, p, mx, sum);
+        const float lse = logf(sum);
+#pragma unroll
+        for (int k = 0; k < K; ++k) lp[k] = (zz[k] - mx) - lse;
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { p[k] = z[k][v]; lp[k] = z[k][v]; }
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float tk = t[k][v];
+        if (tk != -1.0f) {
+          a[k][0] = fmaf(tk, lp[k], a[k][0]);
+          a[k][1] += 1.0f;
+          a[k][2] = fmaf(p[k], tk, a[k][2]);
+          a[k][3] += p[k];
+          a[k][4] += tk;
+        }
+      }
+    }
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const float v = warp_sum(a[k][j]);
+      if (lane == 0) red[warp][k * NS + j] = v;
+    }
+  __syncthreads();
+  if (tid < K * NS) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) acc += (double)red[w][tid];
+    atomicAdd(&stats[(size_t)b * K * NS + tid], acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// finalize: one CTA.  out4 = {CE, Dice, #valid dice samples, #non-NaN CE samples};
+// coef[b][c] = {dCE/dS0, dDice/dS2, dDice/dS3}.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+loss_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ weights, int B, int K,
+                     double smooth, float* __restrict__ out4, float* __restrict__ coef) {
+  constexpr int NS = RHSEG_NSTAT;
+  __shared__ double sh[4][256];
+  const int tid = threadIdx.x;
+  double ce_sum = 0.0, dice_sum = 0.0, n_dice = 0.0, n_ce = 0.0;
+  for (int b = tid; b < B; b += blockDim.x) {
+    const double* st = stats + (size_t)b * K * NS;
+    // CE (losses.py:107-116): sum_c -(w_c * S0 / cnt) / K ; any empty class mask -> NaN -> 1.0
+    double ce = 0.0, I = 0.0, U = 0.0;
+    bool ce_nan = false;
+    for (int c = 0; c < K; ++c) {
+      const double w = (double)weights[c];
+      const double cnt = st[c * NS + 1];
+      if (cnt == 0.0) ce_nan = true;
+      else ce += -(w * st[c * NS + 0]) / cnt;
+      I += w * st[c * NS + 2];
+      U += w * st[c * NS + 3] + w * st[c * NS + 4];
+    }
+    ce = ce / (double)K;
+    if (ce != ce) ce_nan = true;
+    if (ce_nan) ce = 1.0; else n_ce += 1.0;
+    ce_sum += ce;
+    // Dice (losses.py:40-41, :64): 1 - (2I + smooth) / (U + smooth); NaN samples are dropped
+    const double num = 2.0 * I + smooth, den = U + smooth;
+    const double dl = 1.0 - num / den;
+    const bool dice_ok = !(dl != dl);
+    if (dice_ok) { dice_sum += dl; n_dice += 1.0; }
+    for (int c = 0; c < K; ++c) {
+      const double w = (double)weights[c];
+      const double cnt = st[c * NS + 1];
+      float* cf = coef + ((size_t)b * K + c) * 3;
+      cf[0] = ce_nan ? 0.f : (float)(-w / (cnt * (double)K * (double)B));
+      // per-sample derivatives; the 1/n_valid factor is applied below once n_valid is known
+      cf[1] = dice_ok ? (float)(w * (-2.0 / den)) : 0.f;
+      cf[2] = dice_ok ? (float)(w * (num / (den * den))) : 0.f;
+    }
+  }
+  sh[0][tid] = ce_sum; sh[1][tid] = dice_sum; sh[2][tid] = n_dice; sh[3][tid] = n_ce;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sh[j][tid] += sh[j][tid + o];
+    }
+    __syncthreads();
+  }
+  const double nv = sh[2][0];
+  if (tid == 0) {
+    out4[0] = (float)(sh[0][0] / (double)B);
+    out4[1] = nv > 0.0 ? (float)(sh[1][0] / nv) : 0.f;
+    out4[2] = (float)nv;
+    out4[3] = (float)sh[3][0];
+  }
+  const float inv_nv = nv > 0.0 ? (float)(1.0 / nv) : 0.f;
+  for (int i = tid; i < B * K; i += blockDim.x) {
+    coef[(size_t)i * 3 + 1] *= inv_nv;
+    coef[(size_t)i * 3 + 2] *= inv_nv;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// gradient pass: dz = g_ce * dCE/dz + g_dice * dDice/dz
+//   a_c = A_c m_c t_c ; g_c = (B_c t_c + C_c) m_c
+//   logits:  dz_k = (a_k - p_k sum_c a_c) + p_k (g_k - sum_c g_c p_c)
+//   raw:     dz_k = a_k + g_k
+// ------------------------------------------------------------------------------------
+template <int K, int VEC, int THREADS, bool LOGITS>
+__global__ void __launch_bounds__(THREADS)
+loss_bwd_kernel(const float* __restrict__ outs, const float* __restrict__ targets, long t_bstride,
+                long t_cstride, const float* __restrict__ coef, const float* __restrict__ g_ce,
+                const float* __restrict__ g_dice, long N, float* __restrict__ dz) {
+  const int b = blockIdx.y;
+  const long px = ((long)blockIdx.x * THREADS + threadIdx.x) * VEC;
+  if (px >= N) return;
+  const float gce = g_ce ? __ldg(g_ce) : 0.f, gdi = g_dice ? __ldg(g_dice) : 0.f;
+  float A[K], Bc[K], Cc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float* cf = coef + ((size_t)b * K + k) * 3;
+    A[k] = gce * __ldg(cf);
+    Bc[k] = gdi * __ldg(cf + 1);
+    Cc[k] = gdi * __ldg(cf + 2);
+  }
+  const float* ob = outs + (size_t)b * K * N + px;
+  const float* tb = targets + (size_t)b * t_bstride + px;
+  float z[K][VEC], t[K][VEC];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const Vec<VEC> zv = ld_stream<VEC>(ob + (size_t)k * N);
+    const Vec<VEC> tv = ld_cached<VEC>(tb + (size_t)k * t_cstride);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { z[k][v] = zv.v[v]; t[k][v] = tv.v[v]; }
+  }
+  float o[K][VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    float a[K], g[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float tk = t[k][v];
+      const bool m = tk != -1.0f;
+      a[k] = m ? A[k] * tk : 0.f;
+      g[k] = m ? fmaf(Bc[k], tk, Cc[k]) : 0.f;
+    }
+    if constexpr (LOGITS) {
+      float zz[K], p[K], mx, sum, sa = 0.f, sgp = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) zz[k] = z[k][v];
+      full_softmax<K>(zz, p, mx, sum);
+#pragma unroll
+      for (int k = 0; k < K; ++k) { sa += a[k]; sgp = fmaf(g[k], p[k], sgp); }
+#pragma unroll
+      for (int k = 0; k < K; ++k) o[k][v] = (a[k] - p[k] * sa) + p[k] * (g[k] - sgp);
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) o[k][v] = a[k] + g[k];
+    }
+  }
+  float* db = dz + (size_t)b * K * N + px;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    Vec<VEC> r;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r.v[v] = o[k][v];
+    *reinterpret_cast<Vec<VEC>*>(db + (size_t)k * N) = r;  // consumed right away by the head backward
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// consistency sums: per group g, sum_{b,n} | sum_{c in g} cur - prev[parent(g)] |
+// ------------------------------------------------------------------------------------
+template <int K, int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+consistency_kernel(const float* __restrict__ cur, const float* __restrict__ prev, const int32_t* __restrict__ table,
+                   int K_prev, long N, double* __restrict__ sums) {
+  constexpr int NWARP = THREADS / 32;
+  __shared__ float red[NWARP][K];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const LevelInfo li = load_level_info<K>(table);
+  float acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.f;
+  for (long px = ((long)blockIdx.x * THREADS + tid) * VEC; px < N; px += (long)gridDim.x * THREADS * VEC) {
+    float c[K][VEC], gs[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const Vec<VEC> t = ld_cached<VEC>(cur + ((size_t)b * K + k) * N + px);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) c[k][v] = t.v[v];
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float x[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) x[k] = c[k][v];
+      group_sum<K>(x, li.start_mask, gs);
+#pragma unroll
+      for (int k = 0; k < K; ++k) c[k][v] = gs[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if ((li.start_mask >> k) & 1) {
+        const Vec<VEC> pv = ld_cached<VEC>(prev + ((size_t)b * K_prev + li.parent[k]) * N + px);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[k] += fabsf(c[k][v] - pv.v[v]);
+      }
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (tid < K && ((li.start_mask >> tid) & 1)) {
+    double a = 0.0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) a += (double)red[w][tid];
+    atomicAdd(&sums[table[RHSEG_TBL_GROUP_OF + tid]], a);
+  }
+}
+
+static bool can_vec4(const void* a, const void* b, long s0, long s1, long N) {
+  return (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(b) & 15u) == 0) &&
+         (s0 % 4 == 0) && (s1 % 4 == 0);
+}
+
+}  // namespace rhseg
+
+using namespace rhseg;
+
+extern "C" int rhseg_loss_stats(const float* outs, const float* targets, long t_bstride, long t_cstride, int B,
+                                int K, int n_pix, int logits_input, double* stats, void* stream) {
+  if (!outs || !targets || !stats || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  RHSEG_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)B * K * RHSEG_NSTAT, st));
+  const long N = n_pix;
+  constexpr int THREADS = 256, ITER = 4;
+  RHSEG_DISPATCH_K(K, {
+    if (can_vec4(outs, targets, t_bstride, t_cstride, N)) {
+      dim3 grid((unsigned)((N + THREADS * 4 * ITER - 1) / (THREADS * 4 * ITER)), B);
+      if (logits_input) loss_stats_kernel<KK, 4, ITER, THREADS, true><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, N, stats);
+      else loss_stats_kernel<KK, 4, ITER, THREADS, false><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, N, stats);
+    } else {
+      dim3 grid((unsigned)((N + THREADS * ITER - 1) / (THREADS * ITER)), B);
+      if (logits_input) loss_stats_kernel<KK, 1, ITER, THREADS, true><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, N, stats);
+      else loss_stats_kernel<KK, 1, ITER, THREADS, false><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, N, stats);
+    }
+  });
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+extern "C" int rhseg_loss_finalize(const double* stats, const float* weights, int B, int K, double smooth,
+                                   float* out4, float* coef, void* stream) {
+  if (!stats || !weights || !out4 || !coef || B <= 0 || K <= 0) return RHSEG_ERR_ARG;
+  loss_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(stats, weights, B, K, smooth, out4, coef);
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+extern "C" int rhseg_loss_bwd(const float* outs, const float* targets, long t_bstride, long t_cstride,
+                              const float* coef, const float* g_ce, const float* g_dice, int B, int K, int n_pix,
+                              int logits_input, float* dz, void* stream) {
+  if (!outs || !targets || !coef || !dz || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long N = n_pix;
+  constexpr int THREADS = 256;
+  RHSEG_DISPATCH_K(K, {
+    if (can_vec4(outs, targets, t_bstride, t_cstride, N) && ((reinterpret_cast<uintptr_t>(dz) & 15u) == 0)) {
+      dim3 grid((unsigned)((N / 4 + THREADS - 1) / THREADS), B);
+      if (logits_input) loss_bwd_kernel<KK, 4, THREADS, true><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
+      else loss_bwd_kernel<KK, 4, THREADS, false><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
+    } else {
+      dim3 grid((unsigned)((N + THREADS - 1) / THREADS), B);
+      if (logits_input) loss_bwd_kernel<KK, 1, THREADS, true><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
+      else loss_bwd_kernel<KK, 1, THREADS, false><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
+    }
+  });
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+extern "C" int rhseg_consistency_sums(const float* cur, const float* prev, const int32_t* table, int B, int K,
+                                      int K_prev, int n_pix, double* sums, void* stream) {
+  if (!cur || !prev || !table || !sums || B <= 0 || n_pix <= 0 || K_prev <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  RHSEG_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * RHSEG_MAX_K, st));
+  const long N = n_pix;
+  constexpr int THREADS = 256;
+  RHSEG_DISPATCH_K(K, {
+    if (can_vec4(cur, prev, 0, 0, N)) {
+      const long vecs = N / 4;
+      dim3 grid((unsigned)min((long)1024, (vecs + THREADS - 1) / THREADS), B);
+      consistency_kernel<KK, 4, THREADS><<<grid, THREADS, 0, st>>>(cur, prev, table, K_prev, N, sums);
+    } else {
+      dim3 grid((unsigned)min((long)1024, (N + THREADS - 1) / THREADS), B);
+      consistency_kernel<KK, 1, THREADS><<<grid, THREADS, 0, st>>>(cur, prev, table, K_prev, N, sums);
+    }
+  });
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}

@@ -1,0 +1,243 @@
+// Metrics: integer confusion matrix (ProcessClasses + torchmetrics multiclass semantics,
+// Metrics/performance_metrics.py:27-141) and the train-loop prediction glue
+// (train.py:206-231, predictEval.py:409-422).
+#include "common.cuh"
+
+namespace rhseg {
+
+// torch.argmax semantics: first maximum, NaN counts as the maximum.
+__device__ __forceinline__ bool beats(float v, float best) { return (v > best) || (v != v && best == best); }
+
+// class index of one pixel following ProcessClasses (performance_metrics.py:31-47)
+template <int K>
+__device__ __forceinline__ int process_class(const float (&x)[K], bool child) {
+  if (child) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) sum += x[k];
+    float best = (sum == 0.f) ? 1.0f : 0.0f;  // prepended "nothing positive" channel
+    int idx = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (beats(x[k], best)) { best = x[k]; idx = k + 1; }
+    return idx;
+  }
+  float best = x[0];
+  int idx = 0;
+#pragma unroll
+  for (int k = 1; k < K; ++k)
+    if (beats(x[k], best)) { best = x[k]; idx = k; }
+  return idx;
+}
+
+// argmax(softmax(z)) with ATen's op order (train.py:219-221)
+template <int K>
+__device__ __forceinline__ int argmax_softmax(const float (&z)[K]) {
+  float p[K], mx, sum;
+  full_softmax<K>(z, p, mx, sum);
+  float best = p[0];
+  int idx = 0;
+#pragma unroll
+  for (int k = 1; k < K; ++k)
+    if (beats(p[k], best)) { best = p[k]; idx = k; }
+  return idx;
+}
+
+// warp-aggregated histogram update: lanes holding the same cell elect one leader
+__device__ __forceinline__ void hist_add(int* hist, int cell) {
+  const unsigned peers = __match_any_sync(0xffffffffu, cell);
+  if (cell >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[cell], __popc(peers));
+}
+
+// MODE 0: inputs are (probs, targets) exactly as the metric wrappers receive them.
+// MODE 1: inputs are (logits, ternary targets); the train-loop glue is applied on the fly.
+template <int K, int VEC, int ITER, int THREADS, int MODE>
+__global__ void __launch_bounds__(THREADS)
+confusion_kernel(const float* __restrict__ probs, long p_bstride, long p_cstride, const float* __restrict__ targets,
+                 long t_bstride, long t_cstride, long N, int child, unsigned long long* __restrict__ conf) {
+  constexpr int NCMAX = K + 1;
+  __shared__ int hist[NCMAX * NCMAX];
+  const int nc = child ? K + 1 : K;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < nc * nc; i += THREADS) hist[i] = 0;
+  __syncthreads();
+  const float* pb = probs + (size_t)b * p_bstride;
+  const float* tb = targets + (size_t)b * t_bstride;
+  const long chunk0 = (long)blockIdx.x * (THREADS * VEC * ITER);
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const long px = chunk0 + (long)it * THREADS * VEC + (long)tid * VEC;
+    const bool ok = px < N;
+    float p[K][VEC], t[K][VEC];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      Vec<VEC> pv, tv;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { pv.v[v] = 0.f; tv.v[v] = 0.f; }
+      if (ok) {
+        pv = ld_stream<VEC>(pb + (size_t)k * p_cstride + px);
+        tv = ld_stream<VEC>(tb + (size_t)k * t_cstride + px);
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { p[k][v] = pv.v[v]; t[k][v] = tv.v[v]; }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float pr[K], tg[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) { pr[k] = p[k][v]; tg[k] = t[k][v]; }
+      if constexpr (MODE == 1) {
+        const int idx = argmax_softmax<K>(pr);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const bool ign = tg[k] == -1.0f;
+          pr[k] = (k == idx && !ign) ? 1.0f : 0.0f;  // one-hot, zeroed where the target is -1
+          tg[k] = ign ? 0.0f : tg[k];                // eval target
+        }
+      }
+      int cell = -1;
+      if (ok) {
+        const int pc = process_class<K>(pr, child != 0);
+        const int tc = process_class<K>(tg, child != 0);
+        if (!(child && tc == 0)) cell = tc * nc + pc;  // torchmetrics ignore_index=0 on child levels
+      }
+      hist_add(hist, cell);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nc * nc; i += THREADS)
+    if (hist[i]) atomicAdd(&conf[i], (unsigned long long)hist[i]);
+}
+
+template <int K, int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+predict_kernel(const float* __restrict__ logits, const float* __restrict__ targets, long t_bstride, long t_cstride,
+               long N, float* __restrict__ onehot, float* __restrict__ eval_t, int32_t* __restrict__ pred_idx) {
+  const int b = blockIdx.y;
+  const long px = ((long)blockIdx.x * THREADS + threadIdx.x) * VEC;
+  if (px >= N) return;
+  float z[K][VEC], t[K][VEC];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const Vec<VEC> zv = ld_stream<VEC>(logits + ((size_t)b * K + k) * N + px);
+    const Vec<VEC> tv = ld_stream<VEC>(targets + (size_t)b * t_bstride + (size_t)k * t_cstride + px);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { z[k][v] = zv.v[v]; t[k][v] = tv.v[v]; }
+  }
+  int idx[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    float zz[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) zz[k] = z[k][v];
+    idx[v] = argmax_softmax<K>(zz);
+    if (pred_idx) pred_idx[(size_t)b * N + px + v] = idx[v];
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    Vec<VEC> oh, et;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const bool ign = t[k][v] == -1.0f;
+      oh.v[v] = (idx[v] == k && !ign) ? 1.0f : 0.0f;
+      et.v[v] = ign ? 0.0f : t[k][v];
+    }
+    if (onehot) *reinterpret_cast<Vec<VEC>*>(onehot + ((size_t)b * K + k) * N + px) = oh;
+    if (eval_t) *reinterpret_cast<Vec<VEC>*>(eval_t + ((size_t)b * K + k) * N + px) = et;
+  }
+}
+
+// The five per-class ratios from the confusion matrix, with torchmetrics' arithmetic order
+// (int64 -> fp32, then the ratio; zero denominator -> 0):
+//   row 0 F1 = 2tp / (2tp + fn + fp)     row 1 Jaccard = tp / (colsum + rowsum - tp)
+//   row 2 Accuracy(average=None) = tp / (tp + fn)   row 3 Precision = tp / (tp + fp)   row 4 Recall
+__global__ void metric_ratios_kernel(const long long* __restrict__ conf, int nc, float* __restrict__ out) {
+  const int c = threadIdx.x;
+  if (c >= nc) return;
+  long long tp = conf[c * nc + c], row = 0, col = 0;
+  for (int j = 0; j < nc; ++j) { row += conf[c * nc + j]; col += conf[j * nc + c]; }
+  const long long fp = col - tp, fn = row - tp;
+  auto safe = [](float num, float den) { return num / (den == 0.f ? 1.f : den); };
+  const float tpf = (float)tp, fpf = (float)fp, fnf = (float)fn;
+  out[0 * nc + c] = safe(2.0f * tpf, (2.0f * tpf + 1.0f * fnf) + fpf);
+  out[1 * nc + c] = safe(tpf, (float)(col + row - tp));
+  out[2 * nc + c] = safe(tpf, (float)(tp + fn));
+  out[3 * nc + c] = safe(tpf, (float)(tp + fp));
+  out[4 * nc + c] = safe(tpf, (float)(tp + fn));
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int MODE>
+static int confusion_launch(const float* probs, long p_bs, long p_cs, const float* targets, long t_bs, long t_cs,
+                            int B, int K, long N, int child, int64_t* conf, cudaStream_t st) {
+  const int nc = child ? K + 1 : K;
+  RHSEG_CUDA(cudaMemsetAsync(conf, 0, sizeof(int64_t) * nc * nc, st));
+  constexpr int THREADS = 256, ITER = 4;
+  const bool v4 = (N % 4 == 0) && aligned16(probs) && aligned16(targets) && p_bs % 4 == 0 && p_cs % 4 == 0 &&
+                  t_bs % 4 == 0 && t_cs % 4 == 0;
+  auto* c = reinterpret_cast<unsigned long long*>(conf);
+  RHSEG_DISPATCH_K(K, {
+    if (v4) {
+      dim3 grid((unsigned)((N + THREADS * 4 * ITER - 1) / (THREADS * 4 * ITER)), B);
+      confusion_kernel<KK, 4, ITER, THREADS, MODE><<<grid, THREADS, 0, st>>>(probs, p_bs, p_cs, targets, t_bs, t_cs, N, child, c);
+    } else {
+      dim3 grid((unsigned)((N + THREADS * ITER - 1) / (THREADS * ITER)), B);
+      confusion_kernel<KK, 1, ITER, THREADS, MODE><<<grid, THREADS, 0, st>>>(probs, p_bs, p_cs, targets, t_bs, t_cs, N, child, c);
+    }
+  });
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+}  // namespace rhseg
+
+using namespace rhseg;
+
+extern "C" int rhseg_confusion_matrix(const float* probs, long p_bstride, long p_cstride, const float* targets,
+                                      long t_bstride, long t_cstride, int B, int K, int n_pix, int child,
+                                      int64_t* conf, void* stream) {
+  if (!probs || !targets || !conf || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  return confusion_launch<0>(probs, p_bstride, p_cstride, targets, t_bstride, t_cstride, B, K, n_pix, child, conf,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int rhseg_confusion_from_logits(const float* logits, const float* targets, long t_bstride,
+                                           long t_cstride, int B, int K, int n_pix, int child, int64_t* conf,
+                                           void* stream) {
+  if (!logits || !targets || !conf || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  return confusion_launch<1>(logits, (long)K * n_pix, (long)n_pix, targets, t_bstride, t_cstride, B, K, n_pix, child,
+                             conf, (cudaStream_t)stream);
+}
+
+extern "C" int rhseg_predict_onehot(const float* logits, const float* targets, long t_bstride, long t_cstride,
+                                    int B, int K, int n_pix, float* onehot, float* eval_t, int32_t* pred_idx,
+                                    void* stream) {
+  if (!logits || !targets || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long N = n_pix;
+  constexpr int THREADS = 256;
+  const bool v4 = (N % 4 == 0) && aligned16(logits) && aligned16(targets) && t_bstride % 4 == 0 && t_cstride % 4 == 0 &&
+                  aligned16(onehot) && aligned16(eval_t);
+  RHSEG_DISPATCH_K(K, {
+    if (v4) {
+      dim3 grid((unsigned)((N / 4 + THREADS - 1) / THREADS), B);
+      predict_kernel<KK, 4, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, N, onehot, eval_t, pred_idx);
+    } else {
+      dim3 grid((unsigned)((N + THREADS - 1) / THREADS), B);
+      predict_kernel<KK, 1, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, N, onehot, eval_t, pred_idx);
+    }
+  });
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+extern "C" int rhseg_metric_ratios(const int64_t* conf, int nc, float* out5, void* stream) {
+  if (!conf || !out5 || nc < 1 || nc > RHSEG_MAX_K + 1) return RHSEG_ERR_ARG;
+  metric_ratios_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(conf), nc, out5);
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}

@@ -1,0 +1,164 @@
+"""Restrictive-hierarchy head: all levels in ONE autograd node over the C-ABI kernels.
+
+Forward per level (reference: Models/models.py:263-306 UNet, :757-802 HRNet):
+    cond   = mean_{hw} P_{L-1}                     (psum of the previous level's kernel)
+    z_L    = (W_L diag(gamma_b)) f_L + (W_L beta_b + bias_L)      FiLM folded into the 1x1 conv
+    [z_L   = bilinear_up(z_L)]                      HRNet only
+    P_0    = sigmoid(z_0);  P_L = P_parent * softmax_group(z_L)
+Backward runs last level -> first (closed forms in DESIGN.md): the gradient reaching
+P_{L-1} is a per-(sample, channel) constant from the FiLM pool plus, for trees deeper than two
+levels, a per-pixel term from the composition.
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import native
+from .native import call, ptr, stream_of
+from .tree_tables import ClassTree
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise native.NativeError("rhseg_b200 head expects float32 tensors, got %s" % t.dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _HierHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tree: ClassTree, out_size: Optional[Tuple[int, int]], *tensors):
+        n = tree.num_levels
+        feats = [_f32c(t) for t in tensors[0:n]]
+        head_w = [_f32c(t) for t in tensors[n:2 * n]]
+        head_b = [_f32c(t) for t in tensors[2 * n:3 * n]]
+        film_w = [_f32c(t) for t in tensors[3 * n:4 * n - 1]]
+        film_b = [_f32c(t) for t in tensors[4 * n - 1:5 * n - 2]]
+        native.require_cuda(*feats, *head_w, *head_b, *film_w, *film_b)
+        dev = feats[0].device
+        st = stream_of(feats[0])
+        tables = tree.device_tables(dev)
+        B, C, Hf, Wf = feats[0].shape
+        H, W = (Hf, Wf) if out_size is None else (int(out_size[0]), int(out_size[1]))
+        upsampled = (H, W) != (Hf, Wf)
+        n_pix = H * W
+        probs, logits, psums, eff_ws, gbs = [], [], [], [], []
+        for L in range(n):
+            K = tree.head_channels[L]
+            K_prev = tree.head_channels[L - 1] if L > 0 else 0
+            f = feats[L]
+            if tuple(f.shape) != (B, C, Hf, Wf):
+                raise native.NativeError("per-level feature tensors must share one shape")
+            if tuple(head_w[L].shape[:2]) != (K, C):
+                raise native.NativeError("head weight of level %d has shape %s, expected [%d,%d,1,1]"
+                                         % (L, tuple(head_w[L].shape), K, C))
+            eff_w = torch.empty((B, K, C), dtype=torch.float32, device=dev)
+            eff_b = torch.empty((B, K), dtype=torch.float32, device=dev)
+            gb = torch.empty((B, 2 * C), dtype=torch.float32, device=dev) if L > 0 else None
+            call("rhseg_film_fold", ptr(head_w[L]), ptr(head_b[L]),
+                 ptr(film_w[L - 1]) if L > 0 else None, ptr(film_b[L - 1]) if L > 0 else None,
+                 ptr(psums[L - 1]) if L > 0 else None, float(n_pix), B, C, K, K_prev,
+                 ptr(gb), ptr(eff_w), ptr(eff_b), st)
+            z = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
+            p = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
+            psum = torch.empty((B, K), dtype=torch.float64, device=dev)
+            z_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev) if upsampled else None
+            call("rhseg_head_level_fwd", ptr(f), ptr(eff_w), ptr(eff_b),
+                 ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
+                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum), st)
+            probs.append(p); logits.append(z); psums.append(psum); eff_ws.append(eff_w); gbs.append(gb)
+        ctx.tree, ctx.dims, ctx.upsampled = tree, (B, C, Hf, Wf, H, W), upsampled
+        ctx.save_for_backward(*feats, *head_w, *film_w, *logits, *probs, *psums, *eff_ws, *[g for g in gbs if g is not None])
+        ctx.set_materialize_grads(False)
+        outs = tuple(probs) + tuple(logits)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        tree = ctx.tree
+        n = tree.num_levels
+        B, C, Hf, Wf, H, W = ctx.dims
+        sv = ctx.saved_tensors
+        feats, head_w, film_w = sv[0:n], sv[n:2 * n], sv[2 * n:3 * n - 1]
+        o = 3 * n - 1
+        logits, probs, psums, eff_ws = sv[o:o + n], sv[o + n:o + 2 * n], sv[o + 2 * n:o + 3 * n], sv[o + 3 * n:o + 4 * n]
+        gbs = [None] + list(sv[o + 4 * n:o + 5 * n - 1])
+        d_probs, d_logits = grads[0:n], grads[n:2 * n]
+        dev = feats[0].device
+        st = stream_of(feats[0])
+        tables = tree.device_tables(dev)
+        n_pix, n_feat = H * W, Hf * Wf
+
+        d_feats: List[Optional[torch.Tensor]] = [None] * n
+        d_hw: List[Optional[torch.Tensor]] = [None] * n
+        d_hb: List[Optional[torch.Tensor]] = [None] * n
+        d_fw: List[Optional[torch.Tensor]] = [None] * (n - 1)
+        d_fb: List[Optional[torch.Tensor]] = [None] * (n - 1)
+
+        g_uniform = None   # [B,K_L] fp64: dLoss/d(sum_n P_L) * n_pix, from level L+1's FiLM
+        dp_pix = None      # [B,K_L,H,W]: per-pixel dLoss/dP_L (composition of level L+1 and/or user grads)
+        pix_mask = 0
+        for L in range(n - 1, -1, -1):
+            K = tree.head_channels[L]
+            K_prev = tree.head_channels[L - 1] if L > 0 else 0
+            mode = tree.act_mode[L]
+            dz = d_logits[L]
+            if dz is not None:
+                dz = _f32c(dz)
+            if d_probs[L] is not None:  # gradients a caller put directly on the probabilities
+                if dp_pix is None:
+                    dp_pix = _f32c(d_probs[L])
+                else:
+                    dp_pix = dp_pix + d_probs[L]
+                pix_mask = (1 << K) - 1
+            dp_prev, prev_mask = None, 0
+            needs_act = mode != native.ACT_ZEROS and (g_uniform is not None or dp_pix is not None)
+            if needs_act:
+                dz_total = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
+                if mode == native.ACT_GROUPED:
+                    dp_prev = torch.zeros((B, K_prev, H, W), dtype=torch.float32, device=dev)
+                    for pname, _ in tree.child_groups[L - 1]:
+                        prev_mask |= 1 << tree.levels[L - 1].index(pname)
+                call("rhseg_head_act_bwd", ptr(logits[L]), ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
+                     ptr(dz), ptr(g_uniform), 1.0 / n_pix, ptr(dp_pix), pix_mask,
+                     B, K, K_prev, H, W, mode, ptr(dz_total), ptr(dp_prev), st)
+                dz = dz_total
+            g_uniform, dp_pix, pix_mask = None, dp_prev, prev_mask
+            if dz is None:
+                continue  # nothing reaches this level's logits: no gradient for its features / parameters
+            if ctx.upsampled:
+                dz_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev)
+                call("rhseg_upsample_adjoint", ptr(dz), B * K, Hf, Wf, H, W, ptr(dz_lo), st)
+                dz = dz_lo
+            S = torch.empty((B, K, C), dtype=torch.float64, device=dev)
+            s = torch.empty((B, K), dtype=torch.float64, device=dev)
+            if ctx.needs_input_grad[2 + L]:
+                d_feats[L] = torch.empty_like(feats[L])
+            call("rhseg_head_conv_bwd", ptr(feats[L]), ptr(dz), ptr(eff_ws[L]), B, C, K, n_feat,
+                 ptr(d_feats[L]), ptr(S), ptr(s), st)
+            d_hw[L] = torch.empty_like(head_w[L])
+            d_hb[L] = torch.empty((K,), dtype=torch.float32, device=dev)
+            g_prev = None
+            if L > 0:
+                d_fw[L - 1] = torch.empty_like(film_w[L - 1])
+                d_fb[L - 1] = torch.empty((2 * C,), dtype=torch.float32, device=dev)
+                g_prev = torch.empty((B, K_prev), dtype=torch.float64, device=dev)
+            call("rhseg_head_param_grads", ptr(S), ptr(s), ptr(head_w[L]),
+                 ptr(film_w[L - 1]) if L > 0 else None, ptr(gbs[L]), ptr(psums[L - 1]) if L > 0 else None,
+                 float(n_pix), B, C, K, K_prev, ptr(d_hw[L]), ptr(d_hb[L]),
+                 ptr(d_fw[L - 1]) if L > 0 else None, ptr(d_fb[L - 1]) if L > 0 else None, ptr(g_prev), st)
+            g_uniform = g_prev
+        return (None, None) + tuple(d_feats) + tuple(d_hw) + tuple(d_hb) + tuple(d_fw) + tuple(d_fb)
+
+
+def hier_head_forward(tree: ClassTree, feats: Sequence[torch.Tensor],
+                      head_w: Sequence[torch.Tensor], head_b: Sequence[torch.Tensor],
+                      film_w: Sequence[torch.Tensor], film_b: Sequence[torch.Tensor],
+                      out_size: Optional[Tuple[int, int]] = None):
+    """(probs_per_level, logits_per_level), differentiable w.r.t. every input tensor.
+    `feats[L]` is the donor backbone's feature map of its L-th pass [B,C,h,w]; `out_size`
+    (H,W) != (h,w) selects the HRNet path (logits bilinearly upsampled, align_corners=True)."""
+    n = tree.num_levels
+    if not (len(feats) == len(head_w) == len(head_b) == n and len(film_w) == len(film_b) == n - 1):
+        raise native.NativeError("hier_head_forward: expected %d levels of features/heads and %d FiLMs" % (n, n - 1))
+    outs = _HierHeadFn.apply(tree, out_size, *feats, *head_w, *head_b, *film_w, *film_b)
+    return list(outs[:n]), list(outs[n:])

@@ -1,0 +1,112 @@
+"""ctypes binding of librhseg_b200.so (include/rhseg_b200.h).
+
+There is no fallback: if the shared library is missing the first call raises with the
+build command, and every kernel entry point requires CUDA tensors."""
+import ctypes
+import os
+import threading
+
+import torch
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "librhseg_b200.so")
+
+MAX_K = 16
+KERNEL_MAX_K = 8
+TABLE_INTS = 4 + 5 * MAX_K
+NSTAT = 5
+ACT_SIGMOID, ACT_GROUPED, ACT_ZEROS = 0, 1, 2
+
+_c = ctypes
+_P, _I, _L, _D, _U = _c.c_void_p, _c.c_int, _c.c_long, _c.c_double, _c.c_uint32
+
+# name -> argtypes, exactly the prototypes of include/rhseg_b200.h
+SIGNATURES = {
+    "rhseg_abi_version": [],
+    "rhseg_status_string": [_I],
+    "rhseg_device_info": [_P, _P, _P],
+    "rhseg_tree_compile_level": [_P, _I, _I, _P],
+    "rhseg_film_fold": [_P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _P, _P, _P, _P],
+    "rhseg_head_level_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "rhseg_head_act_bwd": [_P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "rhseg_upsample_adjoint": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "rhseg_head_conv_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "rhseg_head_param_grads": [_P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "rhseg_loss_stats": [_P, _P, _L, _L, _I, _I, _I, _I, _P, _P],
+    "rhseg_loss_finalize": [_P, _P, _I, _I, _D, _P, _P, _P],
+    "rhseg_loss_bwd": [_P, _P, _L, _L, _P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "rhseg_consistency_sums": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "rhseg_confusion_matrix": [_P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P, _P],
+    "rhseg_metric_ratios": [_P, _I, _P, _P],
+    "rhseg_predict_onehot": [_P, _P, _L, _L, _I, _I, _I, _P, _P, _P, _P],
+    "rhseg_confusion_from_logits": [_P, _P, _L, _L, _I, _I, _I, _I, _P, _P],
+}
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0  # kernels-launching C-ABI calls issued (bench.py reports it)
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises NativeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise NativeError(
+                        "librhseg_b200.so is missing (%s). Build it with "
+                        "`python -c 'import __graft_entry__ as g; g.build()'` or "
+                        "`python restrictive-hierarchical-semantic-segmentation_b200/build.py`. "
+                        "There is no CPU / PyTorch fallback for this path." % LIB_PATH)
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, argtypes in SIGNATURES.items():
+                    fn = getattr(handle, name)  # AttributeError = symbol missing = broken build
+                    fn.argtypes = argtypes
+                    fn.restype = _c.c_char_p if name == "rhseg_status_string" else _I
+                if handle.rhseg_abi_version() != 1:
+                    raise NativeError("librhseg_b200.so ABI version mismatch; rebuild")
+                _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().rhseg_status_string(rc)
+        raise NativeError("%s failed: %s (status %d)" % (what, msg.decode() if msg else "?", rc))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NativeError("rhseg_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU fallback"
+                              % t.device.type)
+
+
+def call(name, *args):
+    """Invoke one kernel-launching entry point and check its status."""
+    global launch_count
+    launch_count += 1
+    check(getattr(lib(), name)(*args), name)
+
+
+def compile_level_table(parent_ch, k_prev):
+    """Host-side: parent channel list of one level -> int32 table (list of TABLE_INTS ints)."""
+    K = len(parent_ch)
+    src = (_c.c_int32 * K)(*parent_ch)
+    dst = (_c.c_int32 * TABLE_INTS)()
+    check(lib().rhseg_tree_compile_level(src, K, int(k_prev), dst), "rhseg_tree_compile_level")
+    return list(dst)

@@ -1,0 +1,12 @@
+"""Import alias: `import rhseg_b200` loads the package that lives in the (non-identifier)
+directory restrictive-hierarchical-semantic-segmentation_b200/."""
+import importlib.util
+import os
+import sys
+
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "restrictive-hierarchical-semantic-segmentation_b200")
+_spec = importlib.util.spec_from_file_location("rhseg_b200", os.path.join(_DIR, "__init__.py"),
+                                               submodule_search_locations=[_DIR])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["rhseg_b200"] = _mod
+_spec.loader.exec_module(_mod)
