@@ -93,11 +93,13 @@ int rhseg_film_fold(const float* head_w, const float* head_b, const float* film_
  * otherwise: conv at (Hf,Wf) into z_lo [B,K,Hf,Wf] (caller workspace), then one hi-res pass
  * doing upsample + activation.
  * Outputs: logits [B,K,H,W], probs [B,K,H,W], psum [B,K] fp64 = sum over pixels of probs
- * (zeroed here; it is the FiLM pool of the next level).                                   */
+ * (accumulated with atomics: zeroed here when zero_psum != 0, otherwise the caller passes a
+ * zeroed buffer; it is the FiLM pool of the next level).                                  */
 int rhseg_head_level_fwd(const float* feats, const float* eff_w, const float* eff_b,
                          const float* prev_probs, const int32_t* table,
                          int B, int C, int Hf, int Wf, int H, int W, int K, int K_prev, int act_mode,
-                         float* z_lo, float* logits, float* probs, double* psum, void* stream);
+                         float* z_lo, float* logits, float* probs, double* psum, int zero_psum,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (2') head, backward (what autograd does for the reference; closed forms in DESIGN.md).
@@ -121,11 +123,12 @@ int rhseg_upsample_adjoint(const float* dz_hi, int BK, int Hf, int Wf, int H, in
                            float* dz_lo, void* stream);
 
 /* 1x1 conv backward at feature resolution: dfeats[b,c,n] = sum_k eff_w[b,k,c] dz[b,k,n];
- * S[b,k,c] = sum_n dz[b,k,n] feats[b,c,n]; s[b,k] = sum_n dz[b,k,n]  (fp64, zeroed here).
+ * S[b,k,c] = sum_n dz[b,k,n] feats[b,c,n]; s[b,k] = sum_n dz[b,k,n]  (fp64, accumulated with
+ * atomics: zeroed here when zero_sums != 0, otherwise the caller passes zeroed buffers).
  * dfeats may be NULL (features do not require grad).                                      */
 int rhseg_head_conv_bwd(const float* feats, const float* dz, const float* eff_w,
                         int B, int C, int K, int n_pix,
-                        float* dfeats, double* S, double* s, void* stream);
+                        float* dfeats, double* S, double* s, int zero_sums, void* stream);
 
 /* Parameter gradients of one level from S / s (all sums over the batch):
  *   d_head_w [K,C], d_head_b [K]; and when film_w != NULL: d_film_w [2C,K_prev],

@@ -432,12 +432,14 @@ extern "C" int rhseg_upsample_adjoint(const float* dz_hi, int BK, int Hf, int Wf
 }
 
 extern "C" int rhseg_head_conv_bwd(const float* feats, const float* dz, const float* eff_w, int B, int C, int K,
-                                   int n_pix, float* dfeats, double* S, double* s, void* stream) {
+                                   int n_pix, float* dfeats, double* S, double* s, int zero_sums, void* stream) {
   if (!feats || !dz || !eff_w || !S || !s || B <= 0 || C <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  RHSEG_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * (size_t)B * K * C, st));
-  RHSEG_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * (size_t)B * K, st));
+  if (zero_sums) {
+    RHSEG_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * (size_t)B * K * C, st));
+    RHSEG_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * (size_t)B * K, st));
+  }
   const int sms = sm_count();
   RHSEG_DISPATCH_K(K, {
     if (n_pix % 4 == 0) return launch_conv_bwd<KK, 4, (KK <= 4 ? 2 : 1), 256, 4>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);

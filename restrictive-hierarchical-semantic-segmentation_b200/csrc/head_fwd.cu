@@ -429,14 +429,14 @@ extern "C" int rhseg_film_fold(const float* head_w, const float* head_b, const f
 extern "C" int rhseg_head_level_fwd(const float* feats, const float* eff_w, const float* eff_b,
                                     const float* prev_probs, const int32_t* table, int B, int C, int Hf, int Wf,
                                     int H, int W, int K, int K_prev, int act_mode, float* z_lo, float* logits,
-                                    float* probs, double* psum, void* stream) {
+                                    float* probs, double* psum, int zero_psum, void* stream) {
   if (!feats || !eff_w || !eff_b || !logits || !probs || !psum) return RHSEG_ERR_ARG;
   if (B <= 0 || C <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   if (act_mode == RHSEG_ACT_GROUPED && (!prev_probs || !table || K_prev < 1)) return RHSEG_ERR_ARG;
   if (act_mode < 0 || act_mode > RHSEG_ACT_ZEROS) return RHSEG_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  RHSEG_CUDA(cudaMemsetAsync(psum, 0, sizeof(double) * B * K, st));
+  if (zero_psum) RHSEG_CUDA(cudaMemsetAsync(psum, 0, sizeof(double) * B * K, st));
   const bool up = (H != Hf) || (W != Wf);
   const int Nf = Hf * Wf;
   if (!up) {

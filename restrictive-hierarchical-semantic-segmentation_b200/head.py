@@ -42,6 +42,9 @@ class _HierHeadFn(torch.autograd.Function):
         upsampled = (H, W) != (Hf, Wf)
         n_pix = H * W
         probs, logits, psums, eff_ws, gbs = [], [], [], [], []
+        # every level's fp64 pool sums live in one buffer zeroed by a single fill
+        psum_all = torch.zeros((sum(tree.head_channels) * B,), dtype=torch.float64, device=dev)
+        psum_off = 0
         for L in range(n):
             K = tree.head_channels[L]
             K_prev = tree.head_channels[L - 1] if L > 0 else 0
@@ -60,11 +63,12 @@ class _HierHeadFn(torch.autograd.Function):
                  ptr(gb), ptr(eff_w), ptr(eff_b), st)
             z = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
             p = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
-            psum = torch.empty((B, K), dtype=torch.float64, device=dev)
+            psum = psum_all[psum_off:psum_off + B * K].view(B, K)
+            psum_off += B * K
             z_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev) if upsampled else None
             call("rhseg_head_level_fwd", ptr(f), ptr(eff_w), ptr(eff_b),
                  ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
-                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum), st)
+                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum), 0, st)
             probs.append(p); logits.append(z); psums.append(psum); eff_ws.append(eff_w); gbs.append(gb)
         ctx.tree, ctx.dims, ctx.upsampled = tree, (B, C, Hf, Wf, H, W), upsampled
         ctx.save_for_backward(*feats, *head_w, *film_w, *logits, *probs, *psums, *eff_ws, *[g for g in gbs if g is not None])
@@ -94,6 +98,9 @@ class _HierHeadFn(torch.autograd.Function):
         d_fw: List[Optional[torch.Tensor]] = [None] * (n - 1)
         d_fb: List[Optional[torch.Tensor]] = [None] * (n - 1)
 
+        # all fp64 weight-gradient sums (S [B,K,C] and s [B,K] per level) in one zero-filled buffer
+        sums_all = torch.zeros((sum(B * k * (C + 1) for k in tree.head_channels),), dtype=torch.float64, device=dev)
+        sums_off = 0
         g_uniform = None   # [B,K_L] fp64: dLoss/d(sum_n P_L) * n_pix, from level L+1's FiLM
         dp_pix = None      # [B,K_L,H,W]: per-pixel dLoss/dP_L (composition of level L+1 and/or user grads)
         pix_mask = 0
@@ -129,12 +136,13 @@ class _HierHeadFn(torch.autograd.Function):
                 dz_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev)
                 call("rhseg_upsample_adjoint", ptr(dz), B * K, Hf, Wf, H, W, ptr(dz_lo), st)
                 dz = dz_lo
-            S = torch.empty((B, K, C), dtype=torch.float64, device=dev)
-            s = torch.empty((B, K), dtype=torch.float64, device=dev)
+            S = sums_all[sums_off:sums_off + B * K * C].view(B, K, C)
+            s = sums_all[sums_off + B * K * C:sums_off + B * K * (C + 1)].view(B, K)
+            sums_off += B * K * (C + 1)
             if ctx.needs_input_grad[2 + L]:
                 d_feats[L] = torch.empty_like(feats[L])
             call("rhseg_head_conv_bwd", ptr(feats[L]), ptr(dz), ptr(eff_ws[L]), B, C, K, n_feat,
-                 ptr(d_feats[L]), ptr(S), ptr(s), st)
+                 ptr(d_feats[L]), ptr(S), ptr(s), 0, st)
             d_hw[L] = torch.empty_like(head_w[L])
             d_hb[L] = torch.empty((K,), dtype=torch.float32, device=dev)
             g_prev = None

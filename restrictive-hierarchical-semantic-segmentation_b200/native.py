@@ -27,10 +27,10 @@ SIGNATURES = {
     "rhseg_device_info": [_P, _P, _P],
     "rhseg_tree_compile_level": [_P, _I, _I, _P],
     "rhseg_film_fold": [_P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _P, _P, _P, _P],
-    "rhseg_head_level_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "rhseg_head_level_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P],
     "rhseg_head_act_bwd": [_P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "rhseg_upsample_adjoint": [_P, _I, _I, _I, _I, _I, _P, _P],
-    "rhseg_head_conv_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "rhseg_head_conv_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "rhseg_head_param_grads": [_P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "rhseg_loss_stats": [_P, _P, _L, _L, _I, _I, _I, _I, _P, _P],
     "rhseg_loss_finalize": [_P, _P, _I, _I, _D, _P, _P, _P],
