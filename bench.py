@@ -122,8 +122,7 @@ class GpuStep:
         return out
 
     def step(self):
-        for t in self.feats + [p for grp in self.params for p in grp]:
-            t.grad = None
+        self.rh.clear_memo()
         hw, hb, fw, fb = self.params
         probs, logits = self.rh.hier_head_forward(self.tree, self.feats, hw, hb, fw, fb, self.out_size)
         targets = self.targets()
@@ -139,7 +138,8 @@ class GpuStep:
             di = self.rh.level_loss(z, targets[L], w, 0.0, True).dice  # tensor form of SoftDiceLoss (no host sync)
             loss = ce + di if loss is None else loss + ce + di
         loss = loss + self.losses.hierarchical_consistency_loss(onehots, self.tree.levels, self.tree.parent_of)
-        loss.backward()
+        leaves = self.feats + [p for grp in self.params for p in grp]
+        self.grads = torch.autograd.grad(loss, leaves)  # dfeats per level + head / FiLM parameter grads
         self.result = (loss.detach(), ratios)
         return self.result
 
@@ -243,7 +243,7 @@ def run_ours(args, rank, world, local_rank):
             return
         loss, ratios = result
         parts = [loss.reshape(1).double()] + [r.flatten().double() for r in ratios]
-        parts += [p.grad.flatten().double() for grp in st.params for p in grp]
+        parts += [g.flatten().double() for g in st.grads[len(st.feats):]]
         buf = torch.cat(parts)
         torch.distributed.all_reduce(buf)
 
@@ -253,6 +253,12 @@ def run_ours(args, rank, world, local_rank):
     graph = None
     if args.graph:
         try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    st.step()
+            torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

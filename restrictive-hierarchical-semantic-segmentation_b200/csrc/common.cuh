@@ -40,6 +40,17 @@
 
 namespace rhseg {
 
+// SM count of the current device (cached per process; grids are sized from it)
+inline int device_sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached = n > 0 ? n : 148;
+  }
+  return cached;
+}
+
 __host__ __device__ constexpr int pad_k(int K) { return K <= 1 ? 1 : (K <= 2 ? 2 : (K <= 4 ? 4 : 8)); }
 __host__ __device__ constexpr int log2_pow2(int v) { return v <= 1 ? 0 : 1 + log2_pow2(v / 2); }
 

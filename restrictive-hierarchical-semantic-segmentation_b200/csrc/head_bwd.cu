@@ -3,6 +3,7 @@
 // sums) and the tiny parameter-gradient kernel (head conv, FiLM linear, uniform gradient to
 // the previous level's pooled probabilities).  The reference obtains all of this from
 // autograd over Models/models.py:58-77 and :263-306 / :757-802; closed forms in DESIGN.md.
+#include <algorithm>
 #include "common.cuh"
 
 namespace rhseg {
@@ -117,6 +118,10 @@ __device__ __forceinline__ void support(int i, float scale, int out_size, int& l
   hi = min(out_size - 1, (int)ceilf((float)(i + 1) / scale) + 1);
 }
 
+// One thread per low-res element.  The (few) non-zero column weights are hoisted into
+// registers; the row loop then is pure FMA over L1/L2-resident hi-res gradients.
+constexpr int ADJ_MAXS = 12;  // covers upsampling factors up to ~5x; larger factors take the generic loop
+
 __global__ void __launch_bounds__(128)
 upsample_adjoint_kernel(const float* __restrict__ dz_hi, int Hf, int Wf, int H, int W, float sy, float sx,
                         long total, float* __restrict__ dz_lo) {
@@ -130,182 +135,242 @@ upsample_adjoint_kernel(const float* __restrict__ dz_hi, int Hf, int Wf, int H, 
   support(j, sx, W, x0, x1);
   const float* src = dz_hi + (size_t)bk * H * W;
   float acc = 0.f;
-  for (int y = y0; y <= y1; ++y) {
-    const float wy = lerp_weight(y, sy, Hf, i);
-    if (wy == 0.f) continue;
-    float row = 0.f;
-    for (int x = x0; x <= x1; ++x) {
-      const float wx = lerp_weight(x, sx, Wf, j);
-      if (wx != 0.f) row = fmaf(wx, __ldg(src + (size_t)y * W + x), row);
+  if (x1 - x0 + 1 <= ADJ_MAXS) {
+    float wx[ADJ_MAXS];
+#pragma unroll
+    for (int t = 0; t < ADJ_MAXS; ++t) wx[t] = (x0 + t <= x1) ? lerp_weight(x0 + t, sx, Wf, j) : 0.f;
+    for (int y = y0; y <= y1; ++y) {
+      const float wy = lerp_weight(y, sy, Hf, i);
+      if (wy == 0.f) continue;
+      const float* rowp = src + (size_t)y * W + x0;
+      float row = 0.f;
+#pragma unroll
+      for (int t = 0; t < ADJ_MAXS; ++t)
+        if (wx[t] != 0.f) row = fmaf(wx[t], __ldg(rowp + t), row);
+      acc = fmaf(wy, row, acc);
     }
-    acc = fmaf(wy, row, acc);
+  } else {
+    for (int y = y0; y <= y1; ++y) {
+      const float wy = lerp_weight(y, sy, Hf, i);
+      if (wy == 0.f) continue;
+      float row = 0.f;
+      for (int x = x0; x <= x1; ++x) {
+        const float wx = lerp_weight(x, sx, Wf, j);
+        if (wx != 0.f) row = fmaf(wx, __ldg(src + (size_t)y * W + x), row);
+      }
+      acc = fmaf(wy, row, acc);
+    }
   }
   dz_lo[idx] = acc;
 }
 
 // ------------------------------------------------------------------------------------
-// 1x1 conv backward at feature resolution.
-// grid = (pixel chunks, channel slices, B).  Each thread keeps dz for its J*VEC pixels in
-// registers and walks its CTA's channel slice:
+// 1x1 conv backward at feature resolution, persistent CTAs.
+// Work space = (sample, channel slice, pixel-vector), flattened in that order and split EVENLY
+// over one resident wave of CTAs.  Each thread keeps dz for its J*VEC pixels in registers and
+// walks its segment's channel slice:
 //   dfeats[c] = sum_k w[k][c] dz[k]                         (pure write stream)
 //   S[k][c]  += sum_pixels dz[k] * feats[c]                 (read stream + reduction)
 // The per-channel K partial sums are reduced across the warp with the transposed
-// recursive-halving shuffle pattern (KP-1 + 5-log2(KP) shuffles), staged per warp in shared
-// memory, and leave the CTA as one fp64 atomic per (k, c).
+// recursive-halving shuffle pattern (KP-1 + 5-log2(KP) shuffles), accumulated per warp in
+// shared memory over the CTA's tiles, and leave the CTA as one fp64 atomic per (k, c) per
+// (sample, slice) segment.
 // ------------------------------------------------------------------------------------
 template <int K, int VEC, int J, int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS)
 conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, const float* __restrict__ eff_w,
-                int C, int c_per_slice, int N, float* __restrict__ dfeats, double* __restrict__ S,
-                double* __restrict__ s) {
+                int C, int c_per_slice, int slices, int N, long total_work, float* __restrict__ dfeats,
+                double* __restrict__ S, double* __restrict__ s) {
   constexpr int KP = pad_k(K);
   constexpr int P = J * VEC;
   constexpr int NWARP = THREADS / 32;
   extern __shared__ __align__(16) float smem[];
-  const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int c_begin = blockIdx.y * c_per_slice;
-  const int c_cnt = min(c_per_slice, C - c_begin);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* w_t = smem;                               // [c_per_slice][KP]
   float* red = smem + (size_t)c_per_slice * KP;    // [NWARP][c_per_slice][KP]
+  float* my_red = red + (size_t)warp * c_per_slice * KP;
+  const long ups = N / VEC;
+  const long w_begin = total_work * blockIdx.x / gridDim.x;
+  const long w_end = total_work * (blockIdx.x + 1) / gridDim.x;
+  const bool writer = transposed_writer<KP>(lane);
+  const int my_k = transposed_index<KP>(lane);
 
-  for (int i = tid; i < K * c_cnt; i += THREADS) {
-    const int k = i / c_cnt, c = i - k * c_cnt;
-    w_t[c * KP + k] = eff_w[((size_t)b * K + k) * C + c_begin + c];
-  }
-  if constexpr (KP > K)
-    for (int i = tid; i < (KP - K) * c_cnt; i += THREADS) w_t[(i % c_cnt) * KP + K + i / c_cnt] = 0.f;
+  long cur_seg = -1;
+  int b = 0, c_begin = 0, c_cnt = 0;
+  float s_acc = 0.f;  // writer lanes: running sum_n dz[my_k] for the current segment (slice 0 only)
 
-  const long chunk0 = (long)blockIdx.x * (THREADS * P);
-  long px[J];
-  bool ok[J];
-  float g[K][P];
+  auto flush = [&]() {  // uniform: called by the whole CTA
+    __syncthreads();
+    for (int i = tid; i < c_cnt * K; i += THREADS) {
+      const int k = i / c_cnt, c = i - k * c_cnt;
+      double acc = 0.0;
 #pragma unroll
-  for (int j = 0; j < J; ++j) {
-    px[j] = chunk0 + (long)j * THREADS * VEC + (long)tid * VEC;
-    ok[j] = px[j] < N;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      Vec<VEC> t;
-      if (ok[j]) t = ld_cached<VEC>(dz + ((size_t)b * K + k) * N + px[j]);
-      else {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) t.v[v] = 0.f;
-      }
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) g[k][j * VEC + v] = t.v[v];
+      for (int w = 0; w < NWARP; ++w) acc += (double)red[((size_t)w * c_per_slice + c) * KP + k];
+      atomicAdd(&S[((size_t)b * K + k) * C + c_begin + c], acc);
     }
-  }
-  __syncthreads();
-
-  const float* fb = feats + ((size_t)b * C + c_begin) * N;
-  float* dfb = dfeats ? dfeats + ((size_t)b * C + c_begin) * N : nullptr;
-
-  auto one_channel = [&](int cl, const Vec<VEC> (&f)[J]) {
-    float w[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) w[k] = w_t[cl * KP + k];
-    if (dfb) {
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        if (!ok[j]) continue;
-        Vec<VEC> o;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          float a = 0.f;
-#pragma unroll
-          for (int k = 0; k < K; ++k) a = fmaf(w[k], g[k][j * VEC + v], a);
-          o.v[v] = a;
-        }
-        st_stream<VEC>(dfb + (size_t)cl * N + px[j], o);
-      }
-    }
-    float part[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      part[k] = 0.f;
-      if (k < K) {
-#pragma unroll
-        for (int j = 0; j < J; ++j)
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) part[k] = fmaf(g[k][j * VEC + v], f[j].v[v], part[k]);
-      }
-    }
-    warp_reduce_transposed<KP>(part, lane);
-    if (transposed_writer<KP>(lane)) red[((size_t)warp * c_per_slice + cl) * KP + transposed_index<KP>(lane)] = part[0];
+    if (c_begin == 0 && writer && my_k < K) atomicAdd(&s[b * K + my_k], (double)s_acc);
+    __syncthreads();
   };
 
-  int cl = 0;
-  for (; cl + UNROLL <= c_cnt; cl += UNROLL) {
-    Vec<VEC> f[UNROLL][J];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        if (ok[j]) f[u][j] = ld_stream<VEC>(fb + (size_t)(cl + u) * N + px[j]);
-        else {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) f[u][j].v[v] = 0.f;
-        }
+  long w0 = w_begin;
+  while (w0 < w_end) {
+    const long seg = w0 / ups;  // = b * slices + slice
+    const long seg_end = min(w_end, (seg + 1) * ups);
+    const long tile_end = min(seg_end, w0 + (long)THREADS * J);
+    if (seg != cur_seg) {
+      if (cur_seg >= 0) flush();
+      b = (int)(seg / slices);
+      c_begin = (int)(seg % slices) * c_per_slice;
+      c_cnt = min(c_per_slice, C - c_begin);
+      for (int i = tid; i < K * c_cnt; i += THREADS) {
+        const int k = i / c_cnt, c = i - k * c_cnt;
+        w_t[c * KP + k] = eff_w[((size_t)b * K + k) * C + c_begin + c];
       }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) one_channel(cl + u, f[u]);
-  }
-  for (; cl < c_cnt; ++cl) {
-    Vec<VEC> f[J];
+      if constexpr (KP > K)
+        for (int i = tid; i < (KP - K) * c_cnt; i += THREADS) w_t[(i % c_cnt) * KP + K + i / c_cnt] = 0.f;
+      for (int i = tid; i < NWARP * c_per_slice * KP; i += THREADS) red[i] = 0.f;
+      s_acc = 0.f;
+      cur_seg = seg;
+      __syncthreads();
+    }
+
+    long px[J];
+    bool ok[J];
+    float g[K][P];
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      if (ok[j]) f[j] = ld_stream<VEC>(fb + (size_t)cl * N + px[j]);
-      else {
+      const long u = w0 + (long)j * THREADS + tid;
+      ok[j] = u < tile_end;
+      px[j] = (u - seg * ups) * VEC;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) f[j].v[v] = 0.f;
+      for (int k = 0; k < K; ++k) {
+        Vec<VEC> t;
+        if (ok[j]) t = ld_cached<VEC>(dz + ((size_t)b * K + k) * N + px[j]);
+        else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) t.v[v] = 0.f;
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) g[k][j * VEC + v] = t.v[v];
       }
     }
-    one_channel(cl, f);
-  }
 
-  // s[b][k] = sum_n dz: only the first channel slice contributes
-  float sred[KP];
-  if (blockIdx.y == 0) {
+    const float* fb = feats + ((size_t)b * C + c_begin) * N;
+    float* dfb = dfeats ? dfeats + ((size_t)b * C + c_begin) * N : nullptr;
+
+    auto one_channel = [&](int cl, const Vec<VEC> (&f)[J]) {
+      float w[KP];
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      sred[k] = 0.f;
-      if (k < K) {
+      for (int k = 0; k < KP; ++k) w[k] = w_t[cl * KP + k];
+      if (dfb) {
 #pragma unroll
-        for (int p = 0; p < P; ++p) sred[k] += g[k][p];
+        for (int j = 0; j < J; ++j) {
+          if (!ok[j]) continue;
+          Vec<VEC> o;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) a = fmaf(w[k], g[k][j * VEC + v], a);
+            o.v[v] = a;
+          }
+          st_stream<VEC>(dfb + (size_t)cl * N + px[j], o);
+        }
       }
-    }
-    warp_reduce_transposed<KP>(sred, lane);
-  }
-  __syncthreads();
-  for (int i = tid; i < c_cnt * K; i += THREADS) {
-    const int k = i / c_cnt, c = i - k * c_cnt;
-    double acc = 0.0;
+      float part[KP];
 #pragma unroll
-    for (int w = 0; w < NWARP; ++w) acc += (double)red[((size_t)w * c_per_slice + c) * KP + k];
-    atomicAdd(&S[((size_t)b * K + k) * C + c_begin + c], acc);
+      for (int k = 0; k < KP; ++k) {
+        part[k] = 0.f;
+        if (k < K) {
+#pragma unroll
+          for (int j = 0; j < J; ++j)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) part[k] = fmaf(g[k][j * VEC + v], f[j].v[v], part[k]);
+        }
+      }
+      warp_reduce_transposed<KP>(part, lane);
+      if (writer) my_red[cl * KP + my_k] += part[0];
+    };
+
+    int cl = 0;
+    for (; cl + UNROLL <= c_cnt; cl += UNROLL) {
+      Vec<VEC> f[UNROLL][J];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          if (ok[j]) f[u][j] = ld_stream<VEC>(fb + (size_t)(cl + u) * N + px[j]);
+          else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) f[u][j].v[v] = 0.f;
+          }
+        }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) one_channel(cl + u, f[u]);
+    }
+    for (; cl < c_cnt; ++cl) {
+      Vec<VEC> f[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        if (ok[j]) f[j] = ld_stream<VEC>(fb + (size_t)cl * N + px[j]);
+        else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) f[j].v[v] = 0.f;
+        }
+      }
+      one_channel(cl, f);
+    }
+
+    if (c_begin == 0) {  // s[b][k] = sum_n dz: only the first channel slice contributes
+      float sred[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        sred[k] = 0.f;
+        if (k < K) {
+#pragma unroll
+          for (int p = 0; p < P; ++p) sred[k] += g[k][p];
+        }
+      }
+      warp_reduce_transposed<KP>(sred, lane);
+      s_acc += sred[0];
+    }
+    w0 = tile_end;
   }
-  if (blockIdx.y == 0 && transposed_writer<KP>(lane)) {
-    const int k = transposed_index<KP>(lane);
-    if (k < K) atomicAdd(&s[b * K + k], (double)sred[0]);
-  }
+  if (cur_seg >= 0) flush();
 }
 
 template <int K, int VEC, int J, int THREADS, int UNROLL>
 static int launch_conv_bwd(const float* feats, const float* dz, const float* eff_w, int B, int C, int N,
                            float* dfeats, double* S, double* s, int sm_count, cudaStream_t st) {
   constexpr int KP = pad_k(K);
-  const long chunk = (long)THREADS * VEC * J;
-  const int chunks = (int)((N + chunk - 1) / chunk);
-  // split channels until the grid offers >= ~6 CTAs per SM (or slices get shorter than UNROLL*2)
+  auto kern = conv_bwd_kernel<K, VEC, J, THREADS, UNROLL>;
+  const long ups = N / VEC;
+  const long tile = (long)THREADS * J;
+  // channel slices: enough work for >= ~4 tiles per resident CTA, slices no shorter than 2*UNROLL channels
   int slices = 1;
-  while ((long)chunks * B * slices < (long)sm_count * 6 && (C + slices * 2 - 1) / (slices * 2) >= 2 * UNROLL) slices *= 2;
+  auto smem_for = [&](int sl) { return (size_t)((C + sl - 1) / sl) * KP * (1 + THREADS / 32) * sizeof(float); };
+  auto grid_for = [&](int sl, int* per_sm_out) {
+    int per_sm = 0;
+    const size_t smem = smem_for(sl);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm_out) *per_sm_out = per_sm;
+    return (long)sm_count * per_sm;
+  };
+  while ((long)B * ups * slices < grid_for(slices, nullptr) * tile * 4 && (C + slices * 2 - 1) / (slices * 2) >= 2 * UNROLL)
+    slices *= 2;
   const int c_per_slice = (C + slices - 1) / slices;
   slices = (C + c_per_slice - 1) / c_per_slice;
   const size_t smem = (size_t)c_per_slice * KP * (1 + THREADS / 32) * sizeof(float);
-  auto kern = conv_bwd_kernel<K, VEC, J, THREADS, UNROLL>;
   if (smem > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(chunks, slices, B);
-  kern<<<grid, THREADS, smem, st>>>(feats, dz, eff_w, C, c_per_slice, N, dfeats, S, s);
+  int per_sm = 0;
+  RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  const long total_work = (long)B * slices * ups;
+  const long tiles = (total_work + tile - 1) / tile;
+  const long grid = std::min<long>((long)sm_count * per_sm, tiles);
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(feats, dz, eff_w, C, c_per_slice, slices, N, total_work, dfeats, S, s);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }
@@ -370,16 +435,6 @@ param_grads_kernel(const double* __restrict__ S, const double* __restrict__ s, c
   }
 }
 
-static int g_sm_count = 0;
-static int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    g_sm_count = n > 0 ? n : 148;
-  }
-  return g_sm_count;
-}
-
 }  // namespace rhseg
 
 using namespace rhseg;
@@ -440,7 +495,7 @@ extern "C" int rhseg_head_conv_bwd(const float* feats, const float* dz, const fl
     RHSEG_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * (size_t)B * K * C, st));
     RHSEG_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * (size_t)B * K, st));
   }
-  const int sms = sm_count();
+  const int sms = device_sm_count();
   RHSEG_DISPATCH_K(K, {
     if (n_pix % 4 == 0) return launch_conv_bwd<KK, 4, (KK <= 4 ? 2 : 1), 256, 4>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
     return launch_conv_bwd<KK, 1, (KK <= 4 ? 4 : 2), 128, 4>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);

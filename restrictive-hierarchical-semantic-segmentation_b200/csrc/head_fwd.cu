@@ -2,6 +2,7 @@
 // low-resolution conv + fused upsample/activation pass (HRNet).
 // Reference semantics: Models/models.py:58-77 (FiLM), :177-184/:268/:280 (1x1 heads),
 // :269/:288-302 (sigmoid, restrictive softmax, composition, concat), :766/:776 (upsample).
+#include <algorithm>
 #include "common.cuh"
 
 namespace rhseg {
@@ -103,9 +104,11 @@ __device__ __forceinline__ void block_psum(const float (&ps)[K], double* __restr
 }
 
 // ------------------------------------------------------------------------------------
-// Fused 1x1 conv (+ activation).  Each thread owns J vectors of VEC consecutive pixels and
-// walks all C channel planes; the per-sample effective weights sit in shared memory as
-// [C][KP] so that one (vector) broadcast load feeds K*J*VEC FMAs.
+// Fused 1x1 conv (+ activation), persistent CTAs.
+// The flattened (sample, pixel-vector) space is split EVENLY over the grid (one wave, no tail);
+// each CTA walks its range in tiles of THREADS*J vectors.  Each thread owns J vectors of VEC
+// consecutive pixels and walks all C channel planes; the per-sample effective weights sit in
+// shared memory as [C][KP] so that one (vector) broadcast load feeds K*J*VEC FMAs.
 // MODE 3 = conv only (writes `logits` at feature resolution; HRNet low-res pass).
 // ------------------------------------------------------------------------------------
 constexpr int MODE_CONV_ONLY = 3;
@@ -114,157 +117,177 @@ template <int K, int VEC, int J, int MODE, int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS)
 head_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ eff_w,
                 const float* __restrict__ eff_b, const float* __restrict__ prev_probs,
-                const int32_t* __restrict__ table, int C, int N, int K_prev,
+                const int32_t* __restrict__ table, int C, int N, int K_prev, long total_units,
                 float* __restrict__ logits, float* __restrict__ probs, double* __restrict__ psum) {
   constexpr int KP = pad_k(K);
   constexpr int P = J * VEC;
   extern __shared__ __align__(16) float smem[];
   float* w_t = smem;                   // [C][KP]
   float* red = smem + (size_t)C * KP;  // [THREADS/32][K]
-  const int b = blockIdx.y, tid = threadIdx.x;
+  const int tid = threadIdx.x;
+  const long ups = N / VEC;  // vector units per sample (N % VEC == 0 guaranteed by the launcher)
+  const long u_begin = total_units * blockIdx.x / gridDim.x;
+  const long u_end = total_units * (blockIdx.x + 1) / gridDim.x;
 
-  {
-    const float* wsrc = eff_w + (size_t)b * K * C;
-    for (int i = tid; i < K * C; i += THREADS) {
-      const int k = i / C, c = i - k * C;
-      w_t[c * KP + k] = wsrc[i];
-    }
-    if constexpr (KP > K)
-      for (int i = tid; i < (KP - K) * C; i += THREADS) {
-        const int k = K + i / C, c = i % C;
-        w_t[c * KP + k] = 0.f;
-      }
-  }
-  __syncthreads();
+  LevelInfo li;
+  if constexpr (MODE != MODE_CONV_ONLY) li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? table : nullptr);
+  int cur_b = -1;
+  float bias[K], ps[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { bias[k] = 0.f; ps[k] = 0.f; }
 
-  const long chunk0 = (long)blockIdx.x * (THREADS * P);
-  long px[J];
-  bool ok[J];
+  long u0 = u_begin;
+  while (u0 < u_end) {
+    const int b = (int)(u0 / ups);
+    const long seg_end = min(u_end, (long)(b + 1) * ups);
+    const long tile_end = min(seg_end, u0 + (long)THREADS * J);
+    if (b != cur_b) {  // uniform across the CTA
+      if constexpr (MODE != MODE_CONV_ONLY) {
+        if (cur_b >= 0) {
+          block_psum<K, THREADS / 32>(ps, psum + (size_t)cur_b * K, red);
 #pragma unroll
-  for (int j = 0; j < J; ++j) {
-    px[j] = chunk0 + (long)j * THREADS * VEC + (long)tid * VEC;
-    ok[j] = px[j] < N;  // N % VEC == 0 is guaranteed by the launcher
-  }
-
-  float acc[K][P];
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const float bk = eff_b[b * K + k];
-#pragma unroll
-    for (int p = 0; p < P; ++p) acc[k][p] = bk;
-  }
-
-  const float* fb = feats + (size_t)b * C * N;
-  int c0 = 0;
-  for (; c0 + UNROLL <= C; c0 += UNROLL) {
-    Vec<VEC> f[UNROLL][J];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        if (ok[j]) f[u][j] = ld_stream<VEC>(fb + (size_t)(c0 + u) * N + px[j]);
-        else {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) f[u][j].v[v] = 0.f;
+          for (int k = 0; k < K; ++k) ps[k] = 0.f;
         }
       }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      float w[KP];
-      if constexpr (KP == 4) {
-        const float4 t = *reinterpret_cast<const float4*>(w_t + (c0 + u) * KP);
-        w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
-      } else if constexpr (KP == 8) {
-        const float4 t0 = *reinterpret_cast<const float4*>(w_t + (c0 + u) * KP);
-        const float4 t1 = *reinterpret_cast<const float4*>(w_t + (c0 + u) * KP + 4);
-        w[0] = t0.x; w[1] = t0.y; w[2] = t0.z; w[3] = t0.w; w[4] = t1.x; w[5] = t1.y; w[6] = t1.z; w[7] = t1.w;
-      } else if constexpr (KP == 2) {
-        const float2 t = *reinterpret_cast<const float2*>(w_t + (c0 + u) * KP);
-        w[0] = t.x; w[1] = t.y;
-      } else {
-        w[0] = w_t[c0 + u];
+      __syncthreads();
+      const float* wsrc = eff_w + (size_t)b * K * C;
+      for (int i = tid; i < K * C; i += THREADS) {
+        const int k = i / C, c = i - k * C;
+        w_t[c * KP + k] = wsrc[i];
       }
+      if constexpr (KP > K)
+        for (int i = tid; i < (KP - K) * C; i += THREADS) w_t[(i % C) * KP + K + i / C] = 0.f;
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-#pragma unroll
-        for (int j = 0; j < J; ++j)
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[k][j * VEC + v] = fmaf(w[k], f[u][j].v[v], acc[k][j * VEC + v]);
+      for (int k = 0; k < K; ++k) bias[k] = eff_b[b * K + k];
+      cur_b = b;
+      __syncthreads();
     }
-  }
-  for (; c0 < C; ++c0) {
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      if (!ok[j]) continue;
-      const Vec<VEC> f = ld_stream<VEC>(fb + (size_t)c0 * N + px[j]);
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[k][j * VEC + v] = fmaf(w_t[c0 * KP + k], f.v[v], acc[k][j * VEC + v]);
-    }
-  }
 
-  float* zb = logits + (size_t)b * K * N;
-  if constexpr (MODE == MODE_CONV_ONLY) {
+    long px[J];
+    bool ok[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      if (!ok[j]) continue;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        Vec<VEC> o;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) o.v[v] = acc[k][j * VEC + v];
-        *reinterpret_cast<Vec<VEC>*>(zb + (size_t)k * N + px[j]) = o;  // re-read soon: keep cached
-      }
+      const long u = u0 + (long)j * THREADS + tid;
+      ok[j] = u < tile_end;
+      px[j] = (u - (long)b * ups) * VEC;
     }
-    return;
-  } else {
-    const LevelInfo li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? table : nullptr);
-    float pp[K][P];
-    if constexpr (MODE == RHSEG_ACT_GROUPED) {
-      const float* pb = prev_probs + (size_t)b * K_prev * N;
+    float acc[K][P];
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if ((li.start_mask >> k) & 1) {
+    for (int k = 0; k < K; ++k)
 #pragma unroll
-          for (int j = 0; j < J; ++j) {
-            Vec<VEC> t;
-            if (ok[j]) t = ld_cached<VEC>(pb + (size_t)li.parent[k] * N + px[j]);
-            else {
+      for (int p = 0; p < P; ++p) acc[k][p] = bias[k];
+
+    const float* fb = feats + (size_t)b * C * N;
+    int c0 = 0;
+    for (; c0 + UNROLL <= C; c0 += UNROLL) {
+      Vec<VEC> f[UNROLL][J];
 #pragma unroll
-              for (int v = 0; v < VEC; ++v) t.v[v] = 0.f;
-            }
+      for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) pp[k][j * VEC + v] = t.v[v];
+        for (int j = 0; j < J; ++j) {
+          if (ok[j]) f[u][j] = ld_stream<VEC>(fb + (size_t)(c0 + u) * N + px[j]);
+          else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) f[u][j].v[v] = 0.f;
           }
-        } else {
-#pragma unroll
-          for (int p = 0; p < P; ++p) pp[k][p] = pp[k > 0 ? k - 1 : 0][p];
         }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        float w[KP];
+        if constexpr (KP == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(w_t + (c0 + u) * KP);
+          w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+        } else if constexpr (KP == 8) {
+          const float4 t0 = *reinterpret_cast<const float4*>(w_t + (c0 + u) * KP);
+          const float4 t1 = *reinterpret_cast<const float4*>(w_t + (c0 + u) * KP + 4);
+          w[0] = t0.x; w[1] = t0.y; w[2] = t0.z; w[3] = t0.w; w[4] = t1.x; w[5] = t1.y; w[6] = t1.z; w[7] = t1.w;
+        } else if constexpr (KP == 2) {
+          const float2 t = *reinterpret_cast<const float2*>(w_t + (c0 + u) * KP);
+          w[0] = t.x; w[1] = t.y;
+        } else {
+          w[0] = w_t[c0 + u];
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int j = 0; j < J; ++j)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[k][j * VEC + v] = fmaf(w[k], f[u][j].v[v], acc[k][j * VEC + v]);
       }
     }
-    float prob[K][P];
-    activate<K, P, MODE>(acc, pp, li.start_mask, prob);
-    float ps[K];
-    float* pb_out = probs + (size_t)b * K * N;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      ps[k] = 0.f;
+    for (; c0 < C; ++c0) {
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         if (!ok[j]) continue;
-        Vec<VEC> zo, po;
+        const Vec<VEC> f = ld_stream<VEC>(fb + (size_t)c0 * N + px[j]);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          zo.v[v] = acc[k][j * VEC + v];
-          po.v[v] = prob[k][j * VEC + v];
-          ps[k] += po.v[v];
-        }
-        *reinterpret_cast<Vec<VEC>*>(zb + (size_t)k * N + px[j]) = zo;
-        *reinterpret_cast<Vec<VEC>*>(pb_out + (size_t)k * N + px[j]) = po;
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[k][j * VEC + v] = fmaf(w_t[c0 * KP + k], f.v[v], acc[k][j * VEC + v]);
       }
     }
-    block_psum<K, THREADS / 32>(ps, psum + (size_t)b * K, red);
+
+    float* zb = logits + (size_t)b * K * N;
+    if constexpr (MODE == MODE_CONV_ONLY) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        if (!ok[j]) continue;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          Vec<VEC> o;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) o.v[v] = acc[k][j * VEC + v];
+          *reinterpret_cast<Vec<VEC>*>(zb + (size_t)k * N + px[j]) = o;  // re-read soon: keep cached
+        }
+      }
+    } else {
+      float pp[K][P];
+      if constexpr (MODE == RHSEG_ACT_GROUPED) {
+        const float* pb = prev_probs + (size_t)b * K_prev * N;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if ((li.start_mask >> k) & 1) {
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+              Vec<VEC> t;
+              if (ok[j]) t = ld_cached<VEC>(pb + (size_t)li.parent[k] * N + px[j]);
+              else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) t.v[v] = 0.f;
+              }
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) pp[k][j * VEC + v] = t.v[v];
+            }
+          } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) pp[k][p] = pp[k > 0 ? k - 1 : 0][p];
+          }
+        }
+      }
+      float prob[K][P];
+      activate<K, P, MODE>(acc, pp, li.start_mask, prob);
+      float* pb_out = probs + (size_t)b * K * N;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          if (!ok[j]) continue;
+          Vec<VEC> zo, po;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            zo.v[v] = acc[k][j * VEC + v];
+            po.v[v] = prob[k][j * VEC + v];
+            ps[k] += po.v[v];
+          }
+          *reinterpret_cast<Vec<VEC>*>(zb + (size_t)k * N + px[j]) = zo;
+          *reinterpret_cast<Vec<VEC>*>(pb_out + (size_t)k * N + px[j]) = po;
+        }
+      }
+    }
+    u0 = tile_end;
+  }
+  if constexpr (MODE != MODE_CONV_ONLY) {
+    if (cur_b >= 0) block_psum<K, THREADS / 32>(ps, psum + (size_t)cur_b * K, red);
   }
 }
 
@@ -366,9 +389,14 @@ static int launch_fwd(const float* feats, const float* eff_w, const float* eff_b
   const size_t smem = ((size_t)C * KP + (THREADS / 32) * K) * sizeof(float);
   auto kern = head_fwd_kernel<K, VEC, J, MODE, THREADS, UNROLL>;
   if (smem > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long chunk = (long)THREADS * VEC * J;
-  dim3 grid((unsigned)((N + chunk - 1) / chunk), B);
-  kern<<<grid, THREADS, smem, st>>>(feats, eff_w, eff_b, prev_probs, table, C, N, K_prev, logits, probs, psum);
+  int per_sm = 0;
+  RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  const long total_units = (long)B * (N / VEC);
+  const long tiles = (total_units + (long)THREADS * J - 1) / ((long)THREADS * J);
+  const long grid = std::min<long>((long)device_sm_count() * per_sm, tiles);  // one resident wave, evenly split
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(feats, eff_w, eff_b, prev_probs, table, C, N, K_prev, total_units, logits,
+                                             probs, psum);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }

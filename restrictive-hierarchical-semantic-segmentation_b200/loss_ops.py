@@ -107,8 +107,17 @@ class LevelLoss:
         return self.dice if float(self.counts[0].item()) > 0 else None
 
 
-_MEMO = []  # (outs_ref, outs_version, targets_ref, targets_version, key, result)
-_MEMO_MAX = 16
+# (outs_ref, outs_version, targets_ref, targets_version, key, result).  Results carry autograd
+# history, so the memo is kept tiny: the reference calls CE then Dice on the same tensors
+# back to back (train.py:136-137) and one or two live entries cover that.
+_MEMO = []
+_MEMO_MAX = 2
+
+
+def clear_memo():
+    """Drops the memoised level losses (and the autograd history they keep alive)."""
+    del _MEMO[:]
+
 
 
 def level_loss(outs, targets, class_weight, smooth: Optional[float], logits_input: bool) -> LevelLoss:
