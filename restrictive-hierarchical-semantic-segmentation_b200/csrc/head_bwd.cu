@@ -4,7 +4,9 @@
 // the previous level's pooled probabilities).  The reference obtains all of this from
 // autograd over Models/models.py:58-77 and :263-306 / :757-802; closed forms in DESIGN.md.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
+#include "pipeline.cuh"
 
 namespace rhseg {
 
@@ -165,107 +167,223 @@ upsample_adjoint_kernel(const float* __restrict__ dz_hi, int Hf, int Wf, int H, 
 }
 
 // ------------------------------------------------------------------------------------
-// 1x1 conv backward at feature resolution, persistent CTAs.
-// Work space = (sample, channel slice, pixel-vector), flattened in that order and split EVENLY
-// over one resident wave of CTAs.  Each thread keeps dz for its J*VEC pixels in registers and
-// walks its segment's channel slice:
-//   dfeats[c] = sum_k w[k][c] dz[k]                         (pure write stream)
-//   S[k][c]  += sum_pixels dz[k] * feats[c]                 (read stream + reduction)
-// The per-channel K partial sums are reduced across the warp with the transposed
-// recursive-halving shuffle pattern (KP-1 + 5-log2(KP) shuffles), accumulated per warp in
-// shared memory over the CTA's tiles, and leave the CTA as one fp64 atomic per (k, c) per
-// (sample, slice) segment.
+// 1x1 conv backward at feature resolution: TMA-fed, warp-specialised, persistent.
+//
+//   dfeats[b,c,n] = sum_k w[b,k,c] dz[b,k,n]            (pure write stream, registers -> global)
+//   S[b,k,c]      = sum_n dz[b,k,n] feats[b,c,n]        (read stream + reduction)
+//
+// Work unit = (sample, channel stage of PIPE_CH channels, pixel tile), flattened in that order
+// and split EVENLY over one resident wave of CTAs.  The producer warp streams the feature
+// stage of each unit into the shared-memory ring (pipeline.cuh).  A consumer thread owns J
+// vectors of VEC pixels: it re-loads dz for the tile (small, L2-resident) into registers,
+// writes dfeats for the stage's channels, and forms K partial dot products per channel that
+// are reduced across the warp with the transposed recursive-halving shuffle pattern
+// (KP-1 + 5-log2(KP) shuffles).  The per-channel sums of the current (sample, stage) segment
+// stay in registers across tiles and leave the warp as fp64 atomics when the segment ends.
 // ------------------------------------------------------------------------------------
-template <int K, int VEC, int J, int THREADS, int UNROLL>
-__global__ void __launch_bounds__(THREADS)
+template <int K, int VEC, int J, typename CFG>
+__global__ void __launch_bounds__(CFG::THREADS)
 conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, const float* __restrict__ eff_w,
-                int C, int c_per_slice, int slices, int N, long total_work, float* __restrict__ dfeats,
+                int C, int N, int n_tiles, int n_stages, long units_total, int a0, float* __restrict__ dfeats,
                 double* __restrict__ S, double* __restrict__ s) {
   constexpr int KP = pad_k(K);
   constexpr int P = J * VEC;
-  constexpr int NWARP = THREADS / 32;
-  extern __shared__ __align__(16) float smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* w_t = smem;                               // [c_per_slice][KP]
-  float* red = smem + (size_t)c_per_slice * KP;    // [NWARP][c_per_slice][KP]
-  float* my_red = red + (size_t)warp * c_per_slice * KP;
-  const long ups = N / VEC;
-  const long w_begin = total_work * blockIdx.x / gridDim.x;
-  const long w_end = total_work * (blockIdx.x + 1) / gridDim.x;
-  const bool writer = transposed_writer<KP>(lane);
-  const int my_k = transposed_index<KP>(lane);
+  constexpr int NCONS = CFG::CONSUMERS;
+  constexpr int T = NCONS * P;
+  constexpr int ROWP = T + 4;
+  constexpr int CH = CFG::CH;
+  constexpr int NS = CFG::NS;
+  constexpr int FLUSH_TILES = 64;  // fp32 running sums are handed to fp64 at least this often
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // full[NS], empty[NS]
+  float* ring = reinterpret_cast<float*>(smem_raw + 128);  // [NS][CH][ROWP]
+  float* w_all = ring + (size_t)NS * CH * ROWP;            // [NCW][CH][KP] per-warp weights of the current stage
+  static_assert(2 * NS * 8 <= 128, "barrier block");
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long u_begin = units_total * blockIdx.x / gridDim.x;
+  const long u_end = units_total * (blockIdx.x + 1) / gridDim.x;
 
-  long cur_seg = -1;
-  int b = 0, c_begin = 0, c_cnt = 0;
-  float s_acc = 0.f;  // writer lanes: running sum_n dz[my_k] for the current segment (slice 0 only)
-
-  auto flush = [&]() {  // uniform: called by the whole CTA
-    __syncthreads();
-    for (int i = tid; i < c_cnt * K; i += THREADS) {
-      const int k = i / c_cnt, c = i - k * c_cnt;
-      double acc = 0.0;
-#pragma unroll
-      for (int w = 0; w < NWARP; ++w) acc += (double)red[((size_t)w * c_per_slice + c) * KP + k];
-      atomicAdd(&S[((size_t)b * K + k) * C + c_begin + c], acc);
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(smem_u32(&bars[i]), CFG::NPW);
+      mbar_init(smem_u32(&bars[NS + i]), CFG::NCW);
     }
-    if (c_begin == 0 && writer && my_k < K) atomicAdd(&s[b * K + my_k], (double)s_acc);
-    __syncthreads();
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // unit u = (b * n_stages + stage) * n_tiles + tile; decoded once, then advanced incrementally
+  int stage, tile, b;
+  {
+    const long seg0 = u_begin / n_tiles;
+    tile = (int)(u_begin - seg0 * n_tiles);
+    b = (int)(seg0 / n_stages);
+    stage = (int)(seg0 - (long)b * n_stages);
+  }
+  auto advance = [&]() {
+    if (++tile == n_tiles) {
+      tile = 0;
+      if (++stage == n_stages) { stage = 0; ++b; }
+    }
   };
 
-  long w0 = w_begin;
-  while (w0 < w_end) {
-    const long seg = w0 / ups;  // = b * slices + slice
-    const long seg_end = min(w_end, (seg + 1) * ups);
-    const long tile_end = min(seg_end, w0 + (long)THREADS * J);
-    if (seg != cur_seg) {
-      if (cur_seg >= 0) flush();
-      b = (int)(seg / slices);
-      c_begin = (int)(seg % slices) * c_per_slice;
-      c_cnt = min(c_per_slice, C - c_begin);
-      for (int i = tid; i < K * c_cnt; i += THREADS) {
-        const int k = i / c_cnt, c = i - k * c_cnt;
-        w_t[c * KP + k] = eff_w[((size_t)b * K + k) * C + c_begin + c];
+  if (warp >= CFG::NCW) {
+    // ------------------------------ producers ------------------------------
+    if (lane == 0) {
+      const int pw = warp - CFG::NCW;
+      const uint64_t pol = l2_evict_first_policy();
+      int slot = 0;
+      uint32_t phase = 1;
+      for (long u = u_begin; u < u_end; ++u) {
+        mbar_wait(smem_u32(&bars[NS + slot]), phase);
+        const int p0 = tile * T;
+        const int c0 = stage * CH;
+        issue_stage_rows(feats, ((long)b * C + c0) * N + p0, N, min(T, N - p0), min(CH, C - c0), pw, CFG::NPW, a0,
+                         smem_u32(ring + (size_t)slot * CH * ROWP), ROWP * 4, smem_u32(&bars[slot]), pol);
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+        advance();
       }
-      if constexpr (KP > K)
-        for (int i = tid; i < (KP - K) * c_cnt; i += THREADS) w_t[(i % c_cnt) * KP + K + i / c_cnt] = 0.f;
-      for (int i = tid; i < NWARP * c_per_slice * KP; i += THREADS) red[i] = 0.f;
-      s_acc = 0.f;
-      cur_seg = seg;
-      __syncthreads();
     }
+    return;
+  }
 
-    long px[J];
-    bool ok[J];
-    float g[K][P];
+  // -------------------------------- consumers --------------------------------
+  const bool writer = transposed_writer<KP>(lane);
+  const int my_k = transposed_index<KP>(lane);
+  const int sN = N & 3;
+  float* w_s = w_all + (size_t)warp * CH * KP;
+  float sacc[CH];  // writer lanes: running sum over pixels of dz[my_k] * feats[c0 + cc]
+  float s_acc = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < CH; ++cc) sacc[cc] = 0.f;
+  long cur_seg = -1;
+  int seg_b = 0, seg_c0 = 0, seg_cnt = 0, tiles_since_flush = 0;
+
+  auto flush = [&]() {  // per warp, no CTA-wide sync needed: every warp owns its partial sums
+    if (writer && my_k < K) {
+#pragma unroll
+      for (int cc = 0; cc < CH; ++cc)
+        if (cc < seg_cnt) atomicAdd(&S[((size_t)seg_b * K + my_k) * C + seg_c0 + cc], (double)sacc[cc]);
+      if (seg_c0 == 0) atomicAdd(&s[seg_b * K + my_k], (double)s_acc);
+    }
+#pragma unroll
+    for (int cc = 0; cc < CH; ++cc) sacc[cc] = 0.f;
+    s_acc = 0.f;
+    tiles_since_flush = 0;
+  };
+
+  float g_next[K][P];
+  auto load_dz = [&](int bb, int tt) {
+    const int q0 = tt * T;
+    const int q_act = min(T, N - q0);
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const long u = w0 + (long)j * THREADS + tid;
-      ok[j] = u < tile_end;
-      px[j] = (u - seg * ups) * VEC;
+      const int l = (j * NCONS + tid) * VEC;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         Vec<VEC> t;
-        if (ok[j]) t = ld_cached<VEC>(dz + ((size_t)b * K + k) * N + px[j]);
+        if (l < q_act) t = ld_cached<VEC>(dz + ((size_t)bb * K + k) * N + q0 + l);
         else {
 #pragma unroll
           for (int v = 0; v < VEC; ++v) t.v[v] = 0.f;
         }
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) g[k][j * VEC + v] = t.v[v];
+        for (int v = 0; v < VEC; ++v) g_next[k][j * VEC + v] = t.v[v];
       }
     }
+  };
+  if (u_begin < u_end) load_dz(b, tile);
+  int slot = 0;
+  uint32_t phase = 0;
+  for (long u = u_begin; u < u_end; ++u) {
+    const long seg = (long)b * n_stages + stage;
+    const int p0 = tile * T;
+    const int t_act = min(T, N - p0);
+    const int c0 = stage * CH;
+    const int ccnt = min(CH, C - c0);
+    if (seg != cur_seg || tiles_since_flush >= FLUSH_TILES) {
+      if (cur_seg >= 0) flush();
+      if (seg != cur_seg) {  // effective weights of the stage's channels -> this warp's table [CH][KP]
+        __syncwarp();
+        for (int e = lane; e < CH * KP; e += 32) {
+          const int cc = e / KP, k = e - cc * KP;
+          w_s[e] = (cc < ccnt && k < K) ? __ldg(eff_w + ((size_t)b * K + k) * C + c0 + cc) : 0.f;
+        }
+        __syncwarp();
+      }
+      cur_seg = seg; seg_b = b; seg_c0 = c0; seg_cnt = ccnt;
+    }
+    ++tiles_since_flush;
 
-    const float* fb = feats + ((size_t)b * C + c_begin) * N;
-    float* dfb = dfeats ? dfeats + ((size_t)b * C + c_begin) * N : nullptr;
+    // dz of this tile was prefetched during the previous unit; fetch the NEXT unit's dz now so
+    // that its L2 latency hides behind this unit's barrier wait and math
+    int lp[J];
+    bool ok[J];
+    float g[K][P];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      lp[j] = (j * NCONS + tid) * VEC;
+      ok[j] = lp[j] < t_act;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) g[k][j * VEC + v] = g_next[k][j * VEC + v];
+    }
+    if (u + 1 < u_end) {
+      int nt = tile + 1, ns_ = stage, nb = b;
+      if (nt == n_tiles) { nt = 0; if (++ns_ == n_stages) { ns_ = 0; ++nb; } }
+      load_dz(nb, nt);
+    }
 
-    auto one_channel = [&](int cl, const Vec<VEC> (&f)[J]) {
+    int off[4] = {0, 0, 0, 0};
+    int sh0 = 0;
+    if constexpr (VEC == 1) {
+      sh0 = row_shift(((long)b * C + c0) * N + p0, a0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) off[q] = ((sh0 + q * sN) & 3) + tid;
+    }
+    float* dfb = dfeats ? dfeats + ((size_t)b * C + c0) * N + p0 : nullptr;
+    mbar_wait(smem_u32(&bars[slot]), phase);
+    const float* stage_base = ring + (size_t)slot * CH * ROWP;
+
+    // `part` for pixels beyond the tile's end is harmless: their dz registers are zero
+    auto channel = [&](int cc, int offv, float& acc_out) {
+      const float* row = stage_base + cc * ROWP;
       float w[KP];
+      if constexpr (KP == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(w_s + cc * KP);
+        w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+      } else if constexpr (KP == 8) {
+        const float4 t0 = *reinterpret_cast<const float4*>(w_s + cc * KP);
+        const float4 t1 = *reinterpret_cast<const float4*>(w_s + cc * KP + 4);
+        w[0] = t0.x; w[1] = t0.y; w[2] = t0.z; w[3] = t0.w; w[4] = t1.x; w[5] = t1.y; w[6] = t1.z; w[7] = t1.w;
+      } else if constexpr (KP == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(w_s + cc * KP);
+        w[0] = t.x; w[1] = t.y;
+      } else {
+        w[0] = w_s[cc];
+      }
+      float part[KP];
 #pragma unroll
-      for (int k = 0; k < KP; ++k) w[k] = w_t[cl * KP + k];
-      if (dfb) {
+      for (int k = 0; k < KP; ++k) part[k] = 0.f;
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-          if (!ok[j]) continue;
+      for (int j = 0; j < J; ++j) {
+        float f[VEC];
+        if constexpr (VEC == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(row + lp[j]);
+          f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+        } else {
+          f[0] = row[offv + j * NCONS];
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            // NaN-safe masking: stale shared memory past the tile end may hold any bit pattern
+            const float fv = ok[j] ? f[v] : 0.f;
+            part[k] = fmaf(g[k][j * VEC + v], fv, part[k]);
+          }
+        if (dfb && ok[j]) {
           Vec<VEC> o;
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
@@ -274,54 +392,24 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
             for (int k = 0; k < K; ++k) a = fmaf(w[k], g[k][j * VEC + v], a);
             o.v[v] = a;
           }
-          st_stream<VEC>(dfb + (size_t)cl * N + px[j], o);
-        }
-      }
-      float part[KP];
-#pragma unroll
-      for (int k = 0; k < KP; ++k) {
-        part[k] = 0.f;
-        if (k < K) {
-#pragma unroll
-          for (int j = 0; j < J; ++j)
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) part[k] = fmaf(g[k][j * VEC + v], f[j].v[v], part[k]);
+          st_stream<VEC>(dfb + (size_t)cc * N + lp[j], o);
         }
       }
       warp_reduce_transposed<KP>(part, lane);
-      if (writer) my_red[cl * KP + my_k] += part[0];
+      acc_out += part[0];
     };
-
-    int cl = 0;
-    for (; cl + UNROLL <= c_cnt; cl += UNROLL) {
-      Vec<VEC> f[UNROLL][J];
+    if (ccnt == CH) {
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u)
+      for (int cc = 0; cc < CH; ++cc) channel(cc, off[cc & 3], sacc[cc]);
+    } else {
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-          if (ok[j]) f[u][j] = ld_stream<VEC>(fb + (size_t)(cl + u) * N + px[j]);
-          else {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) f[u][j].v[v] = 0.f;
-          }
-        }
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) one_channel(cl + u, f[u]);
+      for (int cc = 0; cc < CH; ++cc)
+        if (cc < ccnt) channel(cc, ((sh0 + cc * sN) & 3) + tid, sacc[cc]);
     }
-    for (; cl < c_cnt; ++cl) {
-      Vec<VEC> f[J];
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        if (ok[j]) f[j] = ld_stream<VEC>(fb + (size_t)cl * N + px[j]);
-        else {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) f[j].v[v] = 0.f;
-        }
-      }
-      one_channel(cl, f);
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bars[NS + slot]));
 
-    if (c_begin == 0) {  // s[b][k] = sum_n dz: only the first channel slice contributes
+    if (c0 == 0) {  // s[b][k] = sum_n dz: only the first channel stage contributes
       float sred[KP];
 #pragma unroll
       for (int k = 0; k < KP; ++k) {
@@ -334,46 +422,39 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
       warp_reduce_transposed<KP>(sred, lane);
       s_acc += sred[0];
     }
-    w0 = tile_end;
+    if (++slot == NS) { slot = 0; phase ^= 1u; }
+    advance();
   }
   if (cur_seg >= 0) flush();
 }
 
-template <int K, int VEC, int J, int THREADS, int UNROLL>
+template <int K, int VEC, int J, typename CFG>
 static int launch_conv_bwd(const float* feats, const float* dz, const float* eff_w, int B, int C, int N,
                            float* dfeats, double* S, double* s, int sm_count, cudaStream_t st) {
   constexpr int KP = pad_k(K);
-  auto kern = conv_bwd_kernel<K, VEC, J, THREADS, UNROLL>;
-  const long ups = N / VEC;
-  const long tile = (long)THREADS * J;
-  // channel slices: enough work for >= ~4 tiles per resident CTA, slices no shorter than 2*UNROLL channels
-  int slices = 1;
-  auto smem_for = [&](int sl) { return (size_t)((C + sl - 1) / sl) * KP * (1 + THREADS / 32) * sizeof(float); };
-  auto grid_for = [&](int sl, int* per_sm_out) {
-    int per_sm = 0;
-    const size_t smem = smem_for(sl);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm_out) *per_sm_out = per_sm;
-    return (long)sm_count * per_sm;
-  };
-  while ((long)B * ups * slices < grid_for(slices, nullptr) * tile * 4 && (C + slices * 2 - 1) / (slices * 2) >= 2 * UNROLL)
-    slices *= 2;
-  const int c_per_slice = (C + slices - 1) / slices;
-  slices = (C + c_per_slice - 1) / c_per_slice;
-  const size_t smem = (size_t)c_per_slice * KP * (1 + THREADS / 32) * sizeof(float);
-  if (smem > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  constexpr int T = CFG::CONSUMERS * J * VEC;
+  const size_t smem = 128 + ((size_t)CFG::NS * CFG::CH * (T + 4) + (size_t)CFG::NCW * CFG::CH * KP) * sizeof(float);
+  auto kern = conv_bwd_kernel<K, VEC, J, CFG>;
+  RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-  if (per_sm < 1) per_sm = 1;
-  const long total_work = (long)B * slices * ups;
-  const long tiles = (total_work + tile - 1) / tile;
-  const long grid = std::min<long>((long)sm_count * per_sm, tiles);
-  kern<<<(unsigned)grid, THREADS, smem, st>>>(feats, dz, eff_w, C, c_per_slice, slices, N, total_work, dfeats, S, s);
+  RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CFG::THREADS, smem));
+  if (per_sm < 1) return RHSEG_ERR_UNSUPPORTED;
+  const int n_tiles = (N + T - 1) / T;
+  const int n_stages = (C + CFG::CH - 1) / CFG::CH;
+  const long units_total = (long)B * n_stages * n_tiles;
+  const long grid = std::max<long>(1, std::min<long>((long)sm_count * per_sm, units_total));
+  const int a0 = (int)((reinterpret_cast<uintptr_t>(feats) >> 2) & 3);
+  kern<<<(unsigned)grid, CFG::THREADS, smem, st>>>(feats, dz, eff_w, C, N, n_tiles, n_stages, units_total, a0, dfeats, S, s);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }
+
+static int tune_env(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+using BwdCfgV4 = PipeCfg<8, 8, 3>;  // 8 consumer warps x float4 -> T = 1024 px, 4 KB row copies, 33 KB stages
+using BwdCfgS1 = PipeCfg<8, 8, 3>;  // scalar rows: T = 256*J px
 
 // ------------------------------------------------------------------------------------
 // parameter gradients (tiny): one thread per feature channel
@@ -497,8 +578,24 @@ extern "C" int rhseg_head_conv_bwd(const float* feats, const float* dz, const fl
   }
   const int sms = device_sm_count();
   RHSEG_DISPATCH_K(K, {
-    if (n_pix % 4 == 0) return launch_conv_bwd<KK, 4, (KK <= 4 ? 2 : 1), 256, 4>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
-    return launch_conv_bwd<KK, 1, (KK <= 4 ? 4 : 2), 128, 4>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+    const bool v4 = (n_pix % 4 == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15u) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(dz) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(dfeats) & 15u) == 0);
+    if (v4) {
+      if constexpr (KK == 4) {
+        const int t = tune_env("RHSEG_TUNE_BWD_V4");
+        if (t == 1) return launch_conv_bwd<KK, 4, 1, PipeCfg<4, 8, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+        if (t == 2) return launch_conv_bwd<KK, 4, 1, PipeCfg<4, 16, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+        if (t == 3) return launch_conv_bwd<KK, 4, 1, PipeCfg<8, 8, 4>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+      }
+      return launch_conv_bwd<KK, 4, 1, BwdCfgV4>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+    }
+    if constexpr (KK == 4) {
+      const int t = tune_env("RHSEG_TUNE_BWD_S1");
+      if (t == 1) return launch_conv_bwd<KK, 1, 2, PipeCfg<8, 8, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+      if (t == 2) return launch_conv_bwd<KK, 1, 4, PipeCfg<4, 8, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+      if (t == 3) return launch_conv_bwd<KK, 1, 2, PipeCfg<8, 16, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+    }
+    return launch_conv_bwd<KK, 1, (KK <= 4 ? 4 : 2), BwdCfgS1>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
   });
   return RHSEG_OK;
 }
