@@ -33,6 +33,7 @@ extern "C" {
 #define RHSEG_KERNEL_MAX_K 8     /* channels per level the fused kernels are built for    */
 #define RHSEG_TABLE_INTS (4 + 5 * RHSEG_MAX_K)
 #define RHSEG_NSTAT 5            /* per (sample, class) loss statistics, see loss_stats   */
+#define RHSEG_MAX_LEVELS 8       /* tree depth rhseg_step_finalize handles in one launch  */
 
 enum {
   RHSEG_OK = 0,
@@ -118,9 +119,21 @@ int rhseg_head_act_bwd(const float* logits, const float* prev_probs, const int32
                        float* dz_out, float* dp_prev, void* stream);
 
 /* Adjoint of the bilinear align_corners=True upsample: dz_hi [B,K,H,W] -> dz_lo [B,K,Hf,Wf]
- * (deterministic gather form).                                                            */
-int rhseg_upsample_adjoint(const float* dz_hi, int BK, int Hf, int Wf, int H, int W,
+ * (deterministic, shared-memory tiled and separable).                                     */
+int rhseg_upsample_adjoint(const float* dz_hi, int B, int K, int Hf, int Wf, int H, int W,
                            float* dz_lo, void* stream);
+
+/* Fused hi-res backward for upsampled heads (HRNet): forms per hi-res pixel
+ *   dz_hi = d(g_ce*CE + g_dice*Dice)/dz  (closed form from logits, targets, coef of
+ *           rhseg_loss_finalize)  +  activation backward of rhseg_head_act_bwd (g_uniform, dp_pix)
+ * and applies the upsample adjoint in the same kernel, so dz_hi is never materialised.
+ * Result dz_lo [B,K,Hf,Wf]; dp_prev (+=) as in rhseg_head_act_bwd.                         */
+int rhseg_head_dz_lowres_fused(const float* logits, const float* targets, long t_bstride, long t_cstride,
+                               const float* coef, const float* g_ce, const float* g_dice,
+                               const float* prev_probs, const int32_t* table, const double* g_uniform,
+                               double inv_npix, const float* dp_pix, uint32_t pix_mask,
+                               int B, int K, int K_prev, int Hf, int Wf, int H, int W, int act_mode,
+                               float* dz_lo, float* dp_prev, void* stream);
 
 /* 1x1 conv backward at feature resolution: dfeats[b,c,n] = sum_k eff_w[b,k,c] dz[b,k,n];
  * S[b,k,c] = sum_n dz[b,k,n] feats[b,c,n]; s[b,k] = sum_n dz[b,k,n]  (fp64, accumulated with
@@ -206,6 +219,37 @@ int rhseg_predict_onehot(const float* logits, const float* targets, long t_bstri
  * to rhseg_predict_onehot followed by rhseg_confusion_matrix, without the one-hot tensors. */
 int rhseg_confusion_from_logits(const float* logits, const float* targets, long t_bstride, long t_cstride,
                                 int B, int K, int n_pix, int child, int64_t* conf, void* stream);
+
+/* Same fused gradient for full-resolution heads (UNet): dz_out [B,K,n_pix] written once. */
+int rhseg_head_dz_fullres_fused(const float* logits, const float* targets, long t_bstride, long t_cstride,
+                                const float* coef, const float* g_ce, const float* g_dice,
+                                const float* prev_probs, const int32_t* table, const double* g_uniform,
+                                double inv_npix, const float* dp_pix, uint32_t pix_mask,
+                                int B, int K, int K_prev, int n_pix, int act_mode,
+                                float* dz_out, float* dp_prev, void* stream);
+
+/* All levels of one training step from the rhseg_level_eval workspaces (stored back to back in
+ * level order), one launch:  out[0] = total = sum_L (CE_L + Dice_L) + consistency
+ * (train.py:132-149), out[1] = consistency, out[2+4L .. 2+4L+3] = rhseg_loss_finalize's out4 of
+ * level L; coef_all = the levels' [B,K_L,3] backward coefficients back to back.
+ * weights_all = the levels' class weights back to back; K_per_level / groups_per_level are HOST
+ * arrays (groups_per_level[0] is ignored).                                                  */
+int rhseg_step_finalize(const void* eval_words, const float* weights_all, int B, int n_levels,
+                        const int32_t* K_per_level, const int32_t* groups_per_level, double smooth,
+                        long n_pix, float* out, float* coef_all, void* stream);
+
+/* Fused per-level TRAINING evaluation (train.py:206-239 for one level in one pass): loss
+ * statistics + train-path prediction + confusion matrix of the masked one-hot prediction +
+ * consistency sums of the masked one-hot predictions against the previous level's.
+ *   parent_targets: the previous level's target slice (strided), prev_idx: its prediction index
+ *   map (uint8 [B,n_pix]) as written by this function for that level; both NULL at level 0.
+ *   out_words (8-byte words, zeroed here):
+ *     [B*K*RHSEG_NSTAT fp64 statistics][RHSEG_MAX_K fp64 consistency sums][nc*nc int64 confusion]
+ *   idx_out: uint8 [B,n_pix] prediction index map (NULL when no deeper level needs it).      */
+int rhseg_level_eval(const float* logits, const float* targets, long t_bstride, long t_cstride,
+                     const float* parent_targets, long pt_bstride, long pt_cstride,
+                     const unsigned char* prev_idx, const int32_t* table, int B, int K, int n_pix,
+                     int child, void* out_words, unsigned char* idx_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -199,6 +199,93 @@ __device__ __forceinline__ void full_softmax(const float (&z)[K], float (&p)[K],
   for (int k = 0; k < K; ++k) p[k] = p[k] / sum;
 }
 
+// ---- per-pixel gradient math shared by the stand-alone and the fused backward kernels ----
+
+// d(g_ce*CE + g_dice*Dice)/dz at one pixel from the closed-form coefficients
+//   a_c = A_c m_c t_c ; g_c = (B_c t_c + C_c) m_c ,  m_c = (t_c != -1)
+//   logits:  dz_k = (a_k - p_k sum_c a_c) + p_k (g_k - sum_c g_c p_c)      raw:  dz_k = a_k + g_k
+template <int K, bool LOGITS>
+__device__ __forceinline__ void loss_dz_pixel(const float (&z)[K], const float (&t)[K], const float (&A)[K],
+                                              const float (&Bc)[K], const float (&Cc)[K], float (&o)[K]) {
+  float a[K], g[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const bool m = t[k] != -1.0f;
+    a[k] = m ? A[k] * t[k] : 0.f;
+    g[k] = m ? fmaf(Bc[k], t[k], Cc[k]) : 0.f;
+  }
+  if constexpr (LOGITS) {
+    float p[K], mx, sum, sa = 0.f, sgp = 0.f;
+    full_softmax<K>(z, p, mx, sum);
+#pragma unroll
+    for (int k = 0; k < K; ++k) { sa += a[k]; sgp = fmaf(g[k], p[k], sgp); }
+#pragma unroll
+    for (int k = 0; k < K; ++k) o[k] = (a[k] - p[k] * sa) + p[k] * (g[k] - sgp);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) o[k] = a[k] + g[k];
+  }
+}
+
+// Activation backward at one pixel: adds the gradient that arrives at the probabilities (dP)
+// to dz, and returns dL/dP_parent per channel (same value for all members of a group).
+//   sigmoid : dz += dP * P (1 - P)
+//   grouped : P_c = P_p * Q_c ; dQ_c = dP_c P_p ; dz += Q (dQ - sum_group dQ Q) ; dP_p = sum_group dP_c Q_c
+// (the log(P_p + eps) gate of the reference contributes exactly zero: softmax is shift invariant)
+template <int K, int MODE>
+__device__ __forceinline__ void act_dz_pixel(const float (&z)[K], const float (&dP)[K], const float (&pp)[K],
+                                             int start_mask, float (&dz)[K], float (&dparent)[K]) {
+  if constexpr (MODE == RHSEG_ACT_SIGMOID) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float p = sigmoidf_ref(z[k]);
+      dz[k] = fmaf(dP[k], p * (1.0f - p), dz[k]);
+      dparent[k] = 0.f;
+    }
+  } else if constexpr (MODE == RHSEG_ACT_GROUPED) {
+    float q[K], dq_q[K], inner[K], dpq[K];
+    grouped_softmax<K>(z, start_mask, q);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      dpq[k] = dP[k] * q[k];
+      dq_q[k] = dpq[k] * pp[k];
+    }
+    group_sum<K>(dq_q, start_mask, inner);
+    group_sum<K>(dpq, start_mask, dparent);
+#pragma unroll
+    for (int k = 0; k < K; ++k) dz[k] += dq_q[k] - q[k] * inner[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) dparent[k] = 0.f;
+  }
+}
+
+// ATen upsample_bilinear2d (align_corners=True) source index / lambdas for one output index
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp make_lerp(int dst, float scale, int in_size) {
+  Lerp r;
+  const float src = scale * (float)dst;
+  r.i0 = (int)src;
+  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.0f - r.l1;
+  return r;
+}
+// weight with which output index `dst` reads input index `want`
+__device__ __forceinline__ float lerp_weight(int dst, float scale, int in_size, int want) {
+  const Lerp l = make_lerp(dst, scale, in_size);
+  return (l.i0 == want ? l.l0 : 0.f) + (l.i1 == want ? l.l1 : 0.f);
+}
+// conservative range [lo, hi] of output indices that read input index i
+__device__ __forceinline__ void lerp_support(int i, float scale, int out_size, int& lo, int& hi) {
+  if (scale <= 0.f) { lo = 0; hi = out_size - 1; return; }
+  lo = max(0, (int)floorf((float)(i - 1) / scale) - 1);
+  hi = min(out_size - 1, (int)ceilf((float)(i + 1) / scale) + 1);
+}
+
 template <int K>
 __device__ __forceinline__ LevelInfo load_level_info(const int32_t* __restrict__ table) {
   LevelInfo li;

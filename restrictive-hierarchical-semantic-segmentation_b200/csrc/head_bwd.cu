@@ -39,16 +39,8 @@ act_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ prev_
     for (int v = 0; v < VEC; ++v) { z[k][v] = t.v[v]; dz[k][v] = d.v[v]; dP[k][v] = gu + e.v[v]; }
   }
 
-  if constexpr (MODE == RHSEG_ACT_SIGMOID) {
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const float p = sigmoidf_ref(z[k][v]);
-        dz[k][v] = fmaf(dP[k][v], p * (1.0f - p), dz[k][v]);
-      }
-  } else if constexpr (MODE == RHSEG_ACT_GROUPED) {
-    float pp[K][VEC];
+  float pp[K][VEC], dpar[K][VEC];
+  if constexpr (MODE == RHSEG_ACT_GROUPED) {
     const float* pb = prev_probs + (size_t)b * K_prev * N + px;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -61,27 +53,17 @@ act_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ prev_
         for (int v = 0; v < VEC; ++v) pp[k][v] = pp[k > 0 ? k - 1 : 0][v];
       }
     }
-    float dpar[K][VEC];
+  }
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      float zz[K], q[K], dq_q[K], inner[K], dpq[K], dparent[K];
+  for (int v = 0; v < VEC; ++v) {
+    float zz[K], dPv[K], ppv[K], dzv[K], dparv[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) zz[k] = z[k][v];
-      grouped_softmax<K>(zz, li.start_mask, q);
+    for (int k = 0; k < K; ++k) { zz[k] = z[k][v]; dPv[k] = dP[k][v]; ppv[k] = pp[k][v]; dzv[k] = dz[k][v]; }
+    act_dz_pixel<K, MODE>(zz, dPv, ppv, li.start_mask, dzv, dparv);
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        dpq[k] = dP[k][v] * q[k];          // P_c = P_p * Q_c  ->  dL/dP_p += dP_c * Q_c
-        dq_q[k] = dpq[k] * pp[k][v];       // dQ_c * Q_c with dQ_c = dP_c * P_p
-      }
-      group_sum<K>(dq_q, li.start_mask, inner);
-      group_sum<K>(dpq, li.start_mask, dparent);
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        // softmax backward inside the group; the log(P_p+eps) gate contributes exactly 0
-        dz[k][v] += dq_q[k] - q[k] * inner[k];
-        dpar[k][v] = dparent[k];
-      }
-    }
+    for (int k = 0; k < K; ++k) { dz[k][v] = dzv[k]; dpar[k][v] = dparv[k]; }
+  }
+  if constexpr (MODE == RHSEG_ACT_GROUPED) {
     if (dp_prev) {
       float* dpb = dp_prev + (size_t)b * K_prev * N + px;
 #pragma unroll
@@ -102,68 +84,6 @@ act_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ prev_
     for (int v = 0; v < VEC; ++v) o.v[v] = dz[k][v];
     *reinterpret_cast<Vec<VEC>*>(dz_out + base + (size_t)k * N) = o;
   }
-}
-
-// ------------------------------------------------------------------------------------
-// adjoint of the bilinear upsample (gather form, deterministic)
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ float lerp_weight(int dst, float scale, int in_size, int want) {
-  const float src = scale * (float)dst;
-  const int i0 = (int)src;
-  const int i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
-  const float l1 = src - (float)i0, l0 = 1.0f - l1;
-  return (i0 == want ? l0 : 0.f) + (i1 == want ? l1 : 0.f);
-}
-__device__ __forceinline__ void support(int i, float scale, int out_size, int& lo, int& hi) {
-  if (scale <= 0.f) { lo = 0; hi = out_size - 1; return; }
-  lo = max(0, (int)floorf((float)(i - 1) / scale) - 1);
-  hi = min(out_size - 1, (int)ceilf((float)(i + 1) / scale) + 1);
-}
-
-// One thread per low-res element.  The (few) non-zero column weights are hoisted into
-// registers; the row loop then is pure FMA over L1/L2-resident hi-res gradients.
-constexpr int ADJ_MAXS = 12;  // covers upsampling factors up to ~5x; larger factors take the generic loop
-
-__global__ void __launch_bounds__(128)
-upsample_adjoint_kernel(const float* __restrict__ dz_hi, int Hf, int Wf, int H, int W, float sy, float sx,
-                        long total, float* __restrict__ dz_lo) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int j = (int)(idx % Wf);
-  const int i = (int)((idx / Wf) % Hf);
-  const long bk = idx / ((long)Wf * Hf);
-  int y0, y1, x0, x1;
-  support(i, sy, H, y0, y1);
-  support(j, sx, W, x0, x1);
-  const float* src = dz_hi + (size_t)bk * H * W;
-  float acc = 0.f;
-  if (x1 - x0 + 1 <= ADJ_MAXS) {
-    float wx[ADJ_MAXS];
-#pragma unroll
-    for (int t = 0; t < ADJ_MAXS; ++t) wx[t] = (x0 + t <= x1) ? lerp_weight(x0 + t, sx, Wf, j) : 0.f;
-    for (int y = y0; y <= y1; ++y) {
-      const float wy = lerp_weight(y, sy, Hf, i);
-      if (wy == 0.f) continue;
-      const float* rowp = src + (size_t)y * W + x0;
-      float row = 0.f;
-#pragma unroll
-      for (int t = 0; t < ADJ_MAXS; ++t)
-        if (wx[t] != 0.f) row = fmaf(wx[t], __ldg(rowp + t), row);
-      acc = fmaf(wy, row, acc);
-    }
-  } else {
-    for (int y = y0; y <= y1; ++y) {
-      const float wy = lerp_weight(y, sy, Hf, i);
-      if (wy == 0.f) continue;
-      float row = 0.f;
-      for (int x = x0; x <= x1; ++x) {
-        const float wx = lerp_weight(x, sx, Wf, j);
-        if (wx != 0.f) row = fmaf(wx, __ldg(src + (size_t)y * W + x), row);
-      }
-      acc = fmaf(wy, row, acc);
-    }
-  }
-  dz_lo[idx] = acc;
 }
 
 // ------------------------------------------------------------------------------------
@@ -551,18 +471,6 @@ extern "C" int rhseg_head_act_bwd(const float* logits, const float* prev_probs, 
         act_bwd_kernel<KK, 1, RHSEG_ACT_ZEROS, THREADS><<<grid, THREADS, 0, st>>>(logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
     }
   });
-  RHSEG_LAUNCH_CHECK();
-  return RHSEG_OK;
-}
-
-extern "C" int rhseg_upsample_adjoint(const float* dz_hi, int BK, int Hf, int Wf, int H, int W, float* dz_lo,
-                                      void* stream) {
-  if (!dz_hi || !dz_lo || BK <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
-  const float sy = H > 1 ? (float)(Hf - 1) / (float)(H - 1) : 0.f;
-  const float sx = W > 1 ? (float)(Wf - 1) / (float)(W - 1) : 0.f;
-  const long total = (long)BK * Hf * Wf;
-  upsample_adjoint_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dz_hi, Hf, Wf, H, W, sy, sx,
-                                                                                           total, dz_lo);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }

@@ -387,20 +387,6 @@ head_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ eff_w
 // the activation.  Index/lambda arithmetic follows ATen's upsample_bilinear2d (fp32 scale =
 // (in-1)/(out-1), src = scale*dst, i0 = (int)src, lambda1 = src - i0).
 // ------------------------------------------------------------------------------------
-struct Lerp {
-  int i0, i1;
-  float l0, l1;
-};
-__device__ __forceinline__ Lerp make_lerp(int dst, float scale, int in_size) {
-  Lerp r;
-  const float src = scale * (float)dst;
-  r.i0 = (int)src;
-  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
-  r.l1 = src - (float)r.i0;
-  r.l0 = 1.0f - r.l1;
-  return r;
-}
-
 template <int K, int VEC, int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 upsample_act_kernel(const float* __restrict__ z_lo, const float* __restrict__ prev_probs,

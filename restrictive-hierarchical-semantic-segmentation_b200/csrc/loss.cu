@@ -91,11 +91,9 @@ loss_stats_kernel(const float* __restrict__ outs, const float* __restrict__ targ
 // finalize: one CTA.  out4 = {CE, Dice, #valid dice samples, #non-NaN CE samples};
 // coef[b][c] = {dCE/dS0, dDice/dS2, dDice/dS3}.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-loss_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ weights, int B, int K,
-                     double smooth, float* __restrict__ out4, float* __restrict__ coef) {
+__device__ void finalize_level(const double* __restrict__ stats, const float* __restrict__ weights, int B, int K,
+                               double smooth, float* __restrict__ out4, float* __restrict__ coef, double (*sh)[256]) {
   constexpr int NS = RHSEG_NSTAT;
-  __shared__ double sh[4][256];
   const int tid = threadIdx.x;
   double ce_sum = 0.0, dice_sum = 0.0, n_dice = 0.0, n_ce = 0.0;
   for (int b = tid; b < B; b += blockDim.x) {
@@ -130,6 +128,7 @@ loss_finalize_kernel(const double* __restrict__ stats, const float* __restrict__
       cf[2] = dice_ok ? (float)(w * (num / (den * den))) : 0.f;
     }
   }
+  __syncthreads();
   sh[0][tid] = ce_sum; sh[1][tid] = dice_sum; sh[2][tid] = n_dice; sh[3][tid] = n_ce;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -150,6 +149,50 @@ loss_finalize_kernel(const double* __restrict__ stats, const float* __restrict__
   for (int i = tid; i < B * K; i += blockDim.x) {
     coef[(size_t)i * 3 + 1] *= inv_nv;
     coef[(size_t)i * 3 + 2] *= inv_nv;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+loss_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ weights, int B, int K,
+                     double smooth, float* __restrict__ out4, float* __restrict__ coef) {
+  __shared__ double sh[4][256];
+  finalize_level(stats, weights, B, K, smooth, out4, coef, sh);
+}
+
+// All levels of one training step in one launch (see rhseg_step_finalize).
+struct StepLevels {
+  int n_levels;
+  int K[RHSEG_MAX_LEVELS];
+  int G[RHSEG_MAX_LEVELS];
+  int child[RHSEG_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(256)
+step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ weights, StepLevels lv, int B,
+                     double smooth, double inv_bn, float* __restrict__ out, float* __restrict__ coef) {
+  __shared__ double sh[4][256];
+  size_t w_off = 0, k_off = 0, c_off = 0;
+  double cons_total = 0.0;
+  int cons_count = 0;
+  for (int L = 0; L < lv.n_levels; ++L) {
+    const int K = lv.K[L];
+    const int nc = lv.child[L] ? K + 1 : K;
+    const double* stats = ws + w_off;
+    finalize_level(stats, weights + k_off, B, K, smooth, out + 2 + 4 * L, coef + c_off, sh);
+    const double* cons = stats + (size_t)B * K * RHSEG_NSTAT;
+    for (int g = 0; g < lv.G[L]; ++g) cons_total += cons[g] * inv_bn;  // mean |children - parent| of group g
+    cons_count += lv.G[L];
+    w_off += (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K + (size_t)nc * nc;
+    k_off += K;
+    c_off += (size_t)B * K * 3;
+  }
+  if (threadIdx.x == 0) {
+    const float cons = cons_count > 0 ? (float)(cons_total / (double)cons_count) : 0.f;
+    float total = cons;
+    for (int L = 0; L < lv.n_levels; ++L) total += out[2 + 4 * L] + out[2 + 4 * L + 1];  // CE_L + Dice_L (0 when none valid)
+    out[0] = total;
+    out[1] = cons;
   }
 }
 
@@ -189,27 +232,12 @@ loss_bwd_kernel(const float* __restrict__ outs, const float* __restrict__ target
   float o[K][VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
-    float a[K], g[K];
+    float zz[K], tt[K], ov[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const float tk = t[k][v];
-      const bool m = tk != -1.0f;
-      a[k] = m ? A[k] * tk : 0.f;
-      g[k] = m ? fmaf(Bc[k], tk, Cc[k]) : 0.f;
-    }
-    if constexpr (LOGITS) {
-      float zz[K], p[K], mx, sum, sa = 0.f, sgp = 0.f;
+    for (int k = 0; k < K; ++k) { zz[k] = z[k][v]; tt[k] = t[k][v]; }
+    loss_dz_pixel<K, LOGITS>(zz, tt, A, Bc, Cc, ov);
 #pragma unroll
-      for (int k = 0; k < K; ++k) zz[k] = z[k][v];
-      full_softmax<K>(zz, p, mx, sum);
-#pragma unroll
-      for (int k = 0; k < K; ++k) { sa += a[k]; sgp = fmaf(g[k], p[k], sgp); }
-#pragma unroll
-      for (int k = 0; k < K; ++k) o[k][v] = (a[k] - p[k] * sa) + p[k] * (g[k] - sgp);
-    } else {
-#pragma unroll
-      for (int k = 0; k < K; ++k) o[k][v] = a[k] + g[k];
-    }
+    for (int k = 0; k < K; ++k) o[k][v] = ov[k];
   }
   float* db = dz + (size_t)b * K * N + px;
 #pragma unroll
@@ -356,6 +384,25 @@ extern "C" int rhseg_consistency_sums(const float* cur, const float* prev, const
       consistency_kernel<KK, 1, THREADS><<<grid, THREADS, 0, st>>>(cur, prev, table, K_prev, N, sums);
     }
   });
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+extern "C" int rhseg_step_finalize(const void* eval_words, const float* weights_all, int B, int n_levels,
+                                   const int32_t* K_per_level, const int32_t* groups_per_level, double smooth,
+                                   long n_pix, float* out, float* coef_all, void* stream) {
+  if (!eval_words || !weights_all || !K_per_level || !groups_per_level || !out || !coef_all) return RHSEG_ERR_ARG;
+  if (B <= 0 || n_levels < 1 || n_levels > RHSEG_MAX_LEVELS || n_pix <= 0) return RHSEG_ERR_ARG;
+  StepLevels lv{};
+  lv.n_levels = n_levels;
+  for (int L = 0; L < n_levels; ++L) {
+    if (K_per_level[L] < 1 || K_per_level[L] > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+    lv.K[L] = K_per_level[L];
+    lv.G[L] = L == 0 ? 0 : groups_per_level[L];
+    lv.child[L] = L == 0 ? 0 : 1;
+  }
+  step_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(eval_words), weights_all, lv, B,
+                                                            smooth, 1.0 / ((double)B * (double)n_pix), out, coef_all);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }

@@ -166,6 +166,158 @@ __global__ void metric_ratios_kernel(const long long* __restrict__ conf, int nc,
   out[4 * nc + c] = safe(tpf, (float)(tp + fn));
 }
 
+// ------------------------------------------------------------------------------------
+// Fused per-level training evaluation: ONE pass over (logits, ternary targets) of a level yields
+//   * the CE/Dice statistics of rhseg_loss_stats                       (Metrics/losses.py:16-134)
+//   * the train-path prediction argmax(softmax(z)) (train.py:219-221), kept only as a uint8 index map
+//   * the confusion matrix of the masked one-hot prediction vs the eval target
+//     (train.py:226-232 + performance_metrics.py:27-141)
+//   * the consistency sums of the masked one-hot predictions against the previous level's
+//     (losses.py:150-177 as train_epoch calls it, train.py:237-239)
+// so neither the one-hot tensors nor the eval targets are ever materialised.
+// out layout (8-byte words): [B*K*5 fp64 stats][RHSEG_MAX_K fp64 consistency sums][nc*nc int64 confusion]
+// ------------------------------------------------------------------------------------
+template <int K, int VEC, int ITER, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ targets, long t_bstride, long t_cstride,
+                  const float* __restrict__ parent_targets, long pt_bstride, long pt_cstride,
+                  const unsigned char* __restrict__ prev_idx, const int32_t* __restrict__ table, long N, int child,
+                  double* __restrict__ stats, double* __restrict__ cons, unsigned long long* __restrict__ conf,
+                  unsigned char* __restrict__ idx_out) {
+  constexpr int NS = RHSEG_NSTAT;
+  constexpr int NWARP = THREADS / 32;
+  constexpr int NACC = K * NS + K;  // statistics + one consistency accumulator per (group start) channel
+  __shared__ float red[NWARP][NACC];
+  __shared__ int hist[(K + 1) * (K + 1)];
+  const int nc = child ? K + 1 : K;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < nc * nc; i += THREADS) hist[i] = 0;
+  __syncthreads();
+  const bool do_cons = child && prev_idx != nullptr && parent_targets != nullptr;
+  const LevelInfo li = load_level_info<K>(child ? table : nullptr);
+  float a[K][NS], ca[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    ca[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) a[k][j] = 0.f;
+  }
+  const float* zb = logits + (size_t)b * K * N;
+  const float* tb = targets + (size_t)b * t_bstride;
+  const long chunk0 = (long)blockIdx.x * (THREADS * VEC * ITER);
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const long px = chunk0 + (long)it * THREADS * VEC + (long)tid * VEC;
+    const bool ok = px < N;
+    float z[K][VEC], t[K][VEC], ptv[K][VEC];
+    unsigned char pidx[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) pidx[v] = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      Vec<VEC> zv, tv;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { zv.v[v] = 0.f; tv.v[v] = -1.f; ptv[k][v] = -1.f; }
+      if (ok) {
+        zv = ld_cached<VEC>(zb + (size_t)k * N + px);
+        tv = ld_cached<VEC>(tb + (size_t)k * t_cstride + px);
+        if (do_cons && ((li.start_mask >> k) & 1)) {
+          const Vec<VEC> pv = ld_cached<VEC>(parent_targets + (size_t)b * pt_bstride + (size_t)li.parent[k] * pt_cstride + px);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) ptv[k][v] = pv.v[v];
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { z[k][v] = zv.v[v]; t[k][v] = tv.v[v]; }
+    }
+    if (ok && do_cons) {
+      if constexpr (VEC == 4) {
+        const uchar4 q = *reinterpret_cast<const uchar4*>(prev_idx + (size_t)b * N + px);
+        pidx[0] = q.x; pidx[1] = q.y; pidx[2] = q.z; pidx[3] = q.w;
+      } else {
+        pidx[0] = prev_idx[(size_t)b * N + px];
+      }
+    }
+    unsigned char my_idx[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float zz[K], p[K], mx, sum;
+#pragma unroll
+      for (int k = 0; k < K; ++k) zz[k] = z[k][v];
+      full_softmax<K>(zz, p, mx, sum);
+      const float lse = logf(sum);
+      // prediction: first maximum of the softmax (torch.argmax semantics)
+      float best = p[0];
+      int idx = 0;
+#pragma unroll
+      for (int k = 1; k < K; ++k)
+        if (beats(p[k], best)) { best = p[k]; idx = k; }
+      my_idx[v] = (unsigned char)idx;
+      float pr[K], et[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float tk = t[k][v];
+        const bool m = tk != -1.0f;
+        if (m && ok) {
+          const float lp = (zz[k] - mx) - lse;
+          a[k][0] = fmaf(tk, lp, a[k][0]);
+          a[k][1] += 1.0f;
+          a[k][2] = fmaf(p[k], tk, a[k][2]);
+          a[k][3] += p[k];
+          a[k][4] += tk;
+        }
+        pr[k] = (k == idx && m) ? 1.0f : 0.0f;
+        et[k] = m ? tk : 0.0f;
+      }
+      int cell = -1;
+      if (ok) {
+        const int pc = process_class<K>(pr, child != 0);
+        const int tc = process_class<K>(et, child != 0);
+        if (!(child && tc == 0)) cell = tc * nc + pc;
+      }
+      hist_add(hist, cell);
+      if (do_cons && ok) {
+        float gs[K];
+        group_sum<K>(pr, li.start_mask, gs);  // children one-hots summed per group
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if ((li.start_mask >> k) & 1) {
+            const float parent_hot = ((int)pidx[v] == li.parent[k] && ptv[k][v] != -1.0f) ? 1.0f : 0.0f;
+            ca[k] += fabsf(gs[k] - parent_hot);
+          }
+      }
+    }
+    if (ok && idx_out) {
+      if constexpr (VEC == 4) {
+        *reinterpret_cast<uchar4*>(idx_out + (size_t)b * N + px) = make_uchar4(my_idx[0], my_idx[1], my_idx[2], my_idx[3]);
+      } else {
+        idx_out[(size_t)b * N + px] = my_idx[0];
+      }
+    }
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const float v = warp_sum(a[k][j]);
+      if (lane == 0) red[warp][k * NS + j] = v;
+    }
+    const float c = warp_sum(ca[k]);
+    if (lane == 0) red[warp][K * NS + k] = c;
+  }
+  __syncthreads();
+  if (tid < NACC) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) acc += (double)red[w][tid];
+    if (tid < K * NS) atomicAdd(&stats[(size_t)b * K * NS + tid], acc);
+    else if (do_cons && ((li.start_mask >> (tid - K * NS)) & 1)) atomicAdd(&cons[table[RHSEG_TBL_GROUP_OF + tid - K * NS]], acc);
+  }
+  for (int i = tid; i < nc * nc; i += THREADS)
+    if (hist[i]) atomicAdd(&conf[i], (unsigned long long)hist[i]);
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int MODE>
@@ -238,6 +390,40 @@ extern "C" int rhseg_predict_onehot(const float* logits, const float* targets, l
 extern "C" int rhseg_metric_ratios(const int64_t* conf, int nc, float* out5, void* stream) {
   if (!conf || !out5 || nc < 1 || nc > RHSEG_MAX_K + 1) return RHSEG_ERR_ARG;
   metric_ratios_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(conf), nc, out5);
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+extern "C" int rhseg_level_eval(const float* logits, const float* targets, long t_bstride, long t_cstride,
+                                const float* parent_targets, long pt_bstride, long pt_cstride,
+                                const unsigned char* prev_idx, const int32_t* table, int B, int K, int n_pix,
+                                int child, void* out_words, unsigned char* idx_out, void* stream) {
+  if (!logits || !targets || !out_words || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  if (child && !table) return RHSEG_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nc = child ? K + 1 : K;
+  const size_t words = (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K + (size_t)nc * nc;
+  RHSEG_CUDA(cudaMemsetAsync(out_words, 0, words * 8, st));
+  double* stats = reinterpret_cast<double*>(out_words);
+  double* cons = stats + (size_t)B * K * RHSEG_NSTAT;
+  unsigned long long* conf = reinterpret_cast<unsigned long long*>(cons + RHSEG_MAX_K);
+  const long N = n_pix;
+  constexpr int THREADS = 256, ITER = 2;
+  bool v4 = (N % 4 == 0) && aligned16(logits) && aligned16(targets) && t_bstride % 4 == 0 && t_cstride % 4 == 0 &&
+            (reinterpret_cast<uintptr_t>(prev_idx) % 4 == 0) && (reinterpret_cast<uintptr_t>(idx_out) % 4 == 0);
+  if (parent_targets) v4 = v4 && aligned16(parent_targets) && pt_bstride % 4 == 0 && pt_cstride % 4 == 0;
+  RHSEG_DISPATCH_K(K, {
+    if (v4) {
+      dim3 grid((unsigned)((N + THREADS * 4 * ITER - 1) / (THREADS * 4 * ITER)), B);
+      level_eval_kernel<KK, 4, ITER, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
+          pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
+    } else {
+      dim3 grid((unsigned)((N + THREADS * ITER - 1) / (THREADS * ITER)), B);
+      level_eval_kernel<KK, 1, ITER, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
+          pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
+    }
+  });
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }

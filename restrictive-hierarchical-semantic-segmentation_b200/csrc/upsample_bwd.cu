@@ -1,0 +1,317 @@
+// Adjoint of the bilinear (align_corners=True) upsample, shared-memory tiled and separable,
+// optionally fused with the hi-res gradient producers (HRNet path).
+//
+// The reference reaches this through autograd over F.interpolate (Models/models.py:766, :776):
+//   dz_lo[i][j] = sum_{y,x} wy(y,i) wx(x,j) dz_hi[y][x]
+// One CTA owns a tile of TH x TW low-res pixels of one sample (all K channels).  It stages the
+// hi-res gradient of the tile's support region in shared memory, reduces along x, then along y.
+// SRC 0: dz_hi is read from memory (what autograd hands us).
+// SRC 1: dz_hi is formed on the fly per hi-res pixel as  loss gradient (closed form from logits,
+//        targets, coefficients) + activation backward (sigmoid / restrictive softmax with the
+//        gradient arriving at the probabilities), so the hi-res gradient tensor never exists.
+#include "common.cuh"
+
+namespace rhseg {
+
+constexpr int ADJ_TH = 8, ADJ_TW = 16, ADJ_THREADS = 256;
+
+struct FusedDzArgs {
+  const float* logits;      // [B,K,H,W]
+  const float* targets;     // strided
+  long t_bstride, t_cstride;
+  const float* coef;        // [B,K,3]
+  const float* g_ce;        // device scalars (may be null)
+  const float* g_dice;
+  const float* prev_probs;  // [B,K_prev,H,W] (grouped)
+  const int32_t* table;
+  const double* g_uniform;  // [B,K] or null
+  float inv_npix;
+  const float* dp_pix;      // [B,K,H,W] or null
+  uint32_t pix_mask;
+  float* dp_prev;           // [B,K_prev,H,W] (+=) or null
+  int K_prev;
+};
+
+template <int K, int SRC, int MODE>
+__global__ void __launch_bounds__(ADJ_THREADS)
+upsample_adjoint_tiled_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, int H, int W, float sy,
+                              float sx, int ry_max, int rx_max, float* __restrict__ dz_lo) {
+  extern __shared__ __align__(16) float sm[];
+  float* reg = sm;                                  // [K][ry_max][rx_max]   hi-res gradient of the support region
+  float* tmp = sm + (size_t)K * ry_max * rx_max;    // [K][ry_max][ADJ_TW]   after the x reduction
+  const int b = blockIdx.z, tid = threadIdx.x;
+  const int i0 = blockIdx.y * ADJ_TH, j0 = blockIdx.x * ADJ_TW;
+  const int th = min(ADJ_TH, Hf - i0), tw = min(ADJ_TW, Wf - j0);
+  int y0, y1, x0, x1, dummy;
+  lerp_support(i0, sy, H, y0, dummy);
+  lerp_support(i0 + th - 1, sy, H, dummy, y1);
+  lerp_support(j0, sx, W, x0, dummy);
+  lerp_support(j0 + tw - 1, sx, W, dummy, x1);
+  const int ry = y1 - y0 + 1, rx = x1 - x0 + 1;  // <= ry_max, rx_max by construction of the launcher
+  const long N = (long)H * W;
+
+  // ---- phase 1: hi-res gradient of the region -> shared memory ----
+  if constexpr (SRC == 0) {
+    for (int e = tid; e < K * ry * rx; e += ADJ_THREADS) {
+      const int k = e / (ry * rx);
+      const int r = e - k * (ry * rx);
+      const int yy = r / rx, xx = r - yy * rx;
+      reg[((size_t)k * ry_max + yy) * rx_max + xx] = __ldg(dz_hi + ((size_t)b * K + k) * N + (size_t)(y0 + yy) * W + x0 + xx);
+    }
+  } else {
+    const LevelInfo li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? fa.table : nullptr);
+    const float gce = fa.g_ce ? __ldg(fa.g_ce) : 0.f, gdi = fa.g_dice ? __ldg(fa.g_dice) : 0.f;
+    float A[K], Bc[K], Cc[K], gu[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float* cf = fa.coef + ((size_t)b * K + k) * 3;
+      A[k] = gce * __ldg(cf);
+      Bc[k] = gdi * __ldg(cf + 1);
+      Cc[k] = gdi * __ldg(cf + 2);
+      gu[k] = fa.g_uniform ? (float)fa.g_uniform[b * K + k] * fa.inv_npix : 0.f;
+    }
+    const bool has_act = MODE != RHSEG_ACT_ZEROS && (fa.g_uniform != nullptr || (fa.dp_pix != nullptr && fa.pix_mask != 0));
+    for (int r = tid; r < ry * rx; r += ADJ_THREADS) {
+      const int yy = r / rx, xx = r - yy * rx;
+      const int y = y0 + yy, x = x0 + xx;
+      const size_t px = (size_t)y * W + x;
+      float z[K], t[K], dz[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        z[k] = __ldg(fa.logits + ((size_t)b * K + k) * N + px);
+        t[k] = __ldg(fa.targets + (size_t)b * fa.t_bstride + (size_t)k * fa.t_cstride + px);
+      }
+      loss_dz_pixel<K, true>(z, t, A, Bc, Cc, dz);
+      if (has_act) {
+        float dP[K], pp[K], dpar[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          dP[k] = gu[k];
+          if (fa.dp_pix && ((fa.pix_mask >> k) & 1u)) dP[k] += __ldg(fa.dp_pix + ((size_t)b * K + k) * N + px);
+          pp[k] = 0.f;
+        }
+        if constexpr (MODE == RHSEG_ACT_GROUPED) {
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            pp[k] = ((li.start_mask >> k) & 1) ? __ldg(fa.prev_probs + ((size_t)b * fa.K_prev + li.parent[k]) * N + px)
+                                               : pp[k > 0 ? k - 1 : 0];
+        }
+        act_dz_pixel<K, MODE>(z, dP, pp, li.start_mask, dz, dpar);
+        if constexpr (MODE == RHSEG_ACT_GROUPED) {
+          // every hi-res pixel is owned by exactly one tile: the one holding floor(src index)
+          if (fa.dp_prev) {
+            const int oi = (int)(sy * (float)y), oj = (int)(sx * (float)x);
+            if (oi >= i0 && oi < i0 + th && oj >= j0 && oj < j0 + tw) {
+#pragma unroll
+              for (int k = 0; k < K; ++k)
+                if ((li.start_mask >> k) & 1) fa.dp_prev[((size_t)b * fa.K_prev + li.parent[k]) * N + px] += dpar[k];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) reg[((size_t)k * ry_max + yy) * rx_max + xx] = dz[k];
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: reduce along x: tmp[k][yy][tj] = sum_x wx(x, j0+tj) reg[k][yy][x] ----
+  for (int e = tid; e < K * ry * tw; e += ADJ_THREADS) {
+    const int tj = e % tw;
+    const int r = e / tw;
+    const int yy = r % ry, k = r / ry;
+    int xa, xb;
+    lerp_support(j0 + tj, sx, W, xa, xb);
+    const float* row = reg + ((size_t)k * ry_max + yy) * rx_max;
+    float acc = 0.f;
+    for (int x = xa; x <= xb; ++x) {
+      const float w = lerp_weight(x, sx, Wf, j0 + tj);
+      if (w != 0.f) acc = fmaf(w, row[x - x0], acc);
+    }
+    tmp[((size_t)k * ry_max + yy) * ADJ_TW + tj] = acc;
+  }
+  __syncthreads();
+
+  // ---- phase 3: reduce along y and store ----
+  for (int e = tid; e < K * th * tw; e += ADJ_THREADS) {
+    const int tj = e % tw;
+    const int r = e / tw;
+    const int ti = r % th, k = r / th;
+    int ya, yb;
+    lerp_support(i0 + ti, sy, H, ya, yb);
+    float acc = 0.f;
+    for (int y = ya; y <= yb; ++y) {
+      const float w = lerp_weight(y, sy, Hf, i0 + ti);
+      if (w != 0.f) acc = fmaf(w, tmp[((size_t)k * ry_max + (y - y0)) * ADJ_TW + tj], acc);
+    }
+    dz_lo[((size_t)b * K + k) * Hf * Wf + (size_t)(i0 + ti) * Wf + j0 + tj] = acc;
+  }
+}
+
+// Full-resolution donors (UNet): the same fused per-pixel gradient, written out once as dz.
+template <int K, int VEC, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+dz_fullres_fused_kernel(FusedDzArgs fa, long N, float* __restrict__ dz_out) {
+  const int b = blockIdx.y;
+  const long px = ((long)blockIdx.x * THREADS + threadIdx.x) * VEC;
+  if (px >= N) return;
+  const LevelInfo li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? fa.table : nullptr);
+  const float gce = fa.g_ce ? __ldg(fa.g_ce) : 0.f, gdi = fa.g_dice ? __ldg(fa.g_dice) : 0.f;
+  float A[K], Bc[K], Cc[K], gu[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float* cf = fa.coef + ((size_t)b * K + k) * 3;
+    A[k] = gce * __ldg(cf);
+    Bc[k] = gdi * __ldg(cf + 1);
+    Cc[k] = gdi * __ldg(cf + 2);
+    gu[k] = fa.g_uniform ? (float)fa.g_uniform[b * K + k] * fa.inv_npix : 0.f;
+  }
+  const bool has_act = MODE != RHSEG_ACT_ZEROS && (fa.g_uniform != nullptr || (fa.dp_pix != nullptr && fa.pix_mask != 0));
+  float z[K][VEC], t[K][VEC], e[K][VEC], pp[K][VEC], o[K][VEC], dpar[K][VEC];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const Vec<VEC> zv = ld_stream<VEC>(fa.logits + ((size_t)b * K + k) * N + px);
+    const Vec<VEC> tv = ld_cached<VEC>(fa.targets + (size_t)b * fa.t_bstride + (size_t)k * fa.t_cstride + px);
+    Vec<VEC> ev;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) ev.v[v] = 0.f;
+    if (has_act && fa.dp_pix && ((fa.pix_mask >> k) & 1u)) ev = ld_stream<VEC>(fa.dp_pix + ((size_t)b * K + k) * N + px);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { z[k][v] = zv.v[v]; t[k][v] = tv.v[v]; e[k][v] = ev.v[v]; pp[k][v] = 0.f; }
+  }
+  if constexpr (MODE == RHSEG_ACT_GROUPED) {
+    if (has_act) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if ((li.start_mask >> k) & 1) {
+          const Vec<VEC> pv = ld_stream<VEC>(fa.prev_probs + ((size_t)b * fa.K_prev + li.parent[k]) * N + px);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) pp[k][v] = pv.v[v];
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) pp[k][v] = pp[k > 0 ? k - 1 : 0][v];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    float zz[K], tt[K], dz[K], dP[K], ppv[K], dpv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { zz[k] = z[k][v]; tt[k] = t[k][v]; dP[k] = gu[k] + e[k][v]; ppv[k] = pp[k][v]; dpv[k] = 0.f; }
+    loss_dz_pixel<K, true>(zz, tt, A, Bc, Cc, dz);
+    if (has_act) act_dz_pixel<K, MODE>(zz, dP, ppv, li.start_mask, dz, dpv);
+#pragma unroll
+    for (int k = 0; k < K; ++k) { o[k][v] = dz[k]; dpar[k][v] = dpv[k]; }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    Vec<VEC> r;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r.v[v] = o[k][v];
+    *reinterpret_cast<Vec<VEC>*>(dz_out + ((size_t)b * K + k) * N + px) = r;  // re-read by the conv backward: keep cached
+  }
+  if constexpr (MODE == RHSEG_ACT_GROUPED) {
+    if (has_act && fa.dp_prev) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if ((li.start_mask >> k) & 1) {
+          float* dst = fa.dp_prev + ((size_t)b * fa.K_prev + li.parent[k]) * N + px;
+          Vec<VEC> cur = *reinterpret_cast<const Vec<VEC>*>(dst);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) cur.v[v] += dpar[k][v];
+          *reinterpret_cast<Vec<VEC>*>(dst) = cur;
+        }
+    }
+  }
+}
+
+// host: worst-case support extent of a tile of `t` inputs (mirrors lerp_support)
+static int region_extent(int t, float scale, int out_size) {
+  if (scale <= 0.f) return out_size;
+  const int e = (int)ceilf((float)(t + 1) / scale) + 5;
+  return e < out_size ? e : out_size;
+}
+
+template <int K, int SRC, int MODE>
+static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int Hf, int Wf, int H, int W, float* dz_lo,
+                          cudaStream_t st) {
+  const float sy = H > 1 ? (float)(Hf - 1) / (float)(H - 1) : 0.f;
+  const float sx = W > 1 ? (float)(Wf - 1) / (float)(W - 1) : 0.f;
+  const int ry_max = region_extent(ADJ_TH, sy, H), rx_max = region_extent(ADJ_TW, sx, W) | 1;  // odd pitch: fewer bank conflicts
+  const size_t smem = ((size_t)K * ry_max * rx_max + (size_t)K * ry_max * ADJ_TW) * sizeof(float);
+  if (smem > 200 * 1024) return RHSEG_ERR_UNSUPPORTED;  // upsampling factor too large for the tiled kernel
+  auto kern = upsample_adjoint_tiled_kernel<K, SRC, MODE>;
+  if (smem > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((Wf + ADJ_TW - 1) / ADJ_TW, (Hf + ADJ_TH - 1) / ADJ_TH, B);
+  kern<<<grid, ADJ_THREADS, smem, st>>>(dz_hi, fa, Hf, Wf, H, W, sy, sx, ry_max, rx_max, dz_lo);
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+}  // namespace rhseg
+
+using namespace rhseg;
+
+extern "C" int rhseg_upsample_adjoint(const float* dz_hi, int B, int K, int Hf, int Wf, int H, int W, float* dz_lo,
+                                      void* stream) {
+  if (!dz_hi || !dz_lo || B <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  FusedDzArgs fa{};
+  RHSEG_DISPATCH_K(K, return (launch_adjoint<KK, 0, 0>(dz_hi, fa, B, Hf, Wf, H, W, dz_lo, (cudaStream_t)stream)));
+  return RHSEG_OK;
+}
+
+extern "C" int rhseg_head_dz_lowres_fused(const float* logits, const float* targets, long t_bstride, long t_cstride,
+                                          const float* coef, const float* g_ce, const float* g_dice,
+                                          const float* prev_probs, const int32_t* table, const double* g_uniform,
+                                          double inv_npix, const float* dp_pix, uint32_t pix_mask, int B, int K,
+                                          int K_prev, int Hf, int Wf, int H, int W, int act_mode, float* dz_lo,
+                                          float* dp_prev, void* stream) {
+  if (!logits || !targets || !coef || !dz_lo || B <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  if (act_mode == RHSEG_ACT_GROUPED && (!prev_probs || !table)) return RHSEG_ERR_ARG;
+  FusedDzArgs fa{logits, targets, t_bstride, t_cstride, coef, g_ce, g_dice, prev_probs, table, g_uniform,
+                 (float)inv_npix, dp_pix, pix_mask, dp_prev, K_prev};
+  cudaStream_t st = (cudaStream_t)stream;
+  RHSEG_DISPATCH_K(K, {
+    if (act_mode == RHSEG_ACT_SIGMOID) return launch_adjoint<KK, 1, RHSEG_ACT_SIGMOID>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, st);
+    if (act_mode == RHSEG_ACT_GROUPED) return launch_adjoint<KK, 1, RHSEG_ACT_GROUPED>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, st);
+    return launch_adjoint<KK, 1, RHSEG_ACT_ZEROS>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, st);
+  });
+  return RHSEG_OK;
+}
+
+extern "C" int rhseg_head_dz_fullres_fused(const float* logits, const float* targets, long t_bstride, long t_cstride,
+                                           const float* coef, const float* g_ce, const float* g_dice,
+                                           const float* prev_probs, const int32_t* table, const double* g_uniform,
+                                           double inv_npix, const float* dp_pix, uint32_t pix_mask, int B, int K,
+                                           int K_prev, int n_pix, int act_mode, float* dz_out, float* dp_prev,
+                                           void* stream) {
+  if (!logits || !targets || !coef || !dz_out || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  if (act_mode == RHSEG_ACT_GROUPED && (!prev_probs || !table)) return RHSEG_ERR_ARG;
+  FusedDzArgs fa{logits, targets, t_bstride, t_cstride, coef, g_ce, g_dice, prev_probs, table, g_uniform,
+                 (float)inv_npix, dp_pix, pix_mask, dp_prev, K_prev};
+  cudaStream_t st = (cudaStream_t)stream;
+  const long N = n_pix;
+  constexpr int THREADS = 256;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool v4 = (N % 4 == 0) && al(logits) && al(targets) && t_bstride % 4 == 0 && t_cstride % 4 == 0 && al(dz_out) &&
+                  al(prev_probs) && al(dp_pix) && al(dp_prev);
+  RHSEG_DISPATCH_K(K, {
+    if (v4) {
+      dim3 grid((unsigned)((N / 4 + THREADS - 1) / THREADS), B);
+      if (act_mode == RHSEG_ACT_SIGMOID) dz_fullres_fused_kernel<KK, 4, RHSEG_ACT_SIGMOID, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
+      else if (act_mode == RHSEG_ACT_GROUPED) dz_fullres_fused_kernel<KK, 4, RHSEG_ACT_GROUPED, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
+      else dz_fullres_fused_kernel<KK, 4, RHSEG_ACT_ZEROS, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
+    } else {
+      dim3 grid((unsigned)((N + THREADS - 1) / THREADS), B);
+      if (act_mode == RHSEG_ACT_SIGMOID) dz_fullres_fused_kernel<KK, 1, RHSEG_ACT_SIGMOID, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
+      else if (act_mode == RHSEG_ACT_GROUPED) dz_fullres_fused_kernel<KK, 1, RHSEG_ACT_GROUPED, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
+      else dz_fullres_fused_kernel<KK, 1, RHSEG_ACT_ZEROS, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
+    }
+  });
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}

@@ -1,0 +1,213 @@
+"""Fused training step of the restrictive-hierarchy path: head forward, train-path prediction,
+confusion-matrix metrics, CE + Dice + consistency loss and the complete backward, as ONE
+autograd node over the sm_100a kernels.
+
+It computes exactly what the body of the reference's train_epoch computes between the donor
+backbone and the optimiser (train.py:201-241: model head -> argmax/one-hot/mask glue ->
+get_metrics -> get_loss -> backward), but
+  * the one-hot prediction and eval-target tensors never exist (rhseg_level_eval reads logits
+    and ternary targets once per level and emits statistics, confusion matrix, consistency sums
+    and a uint8 index map),
+  * the per-level loss gradient, the activation backward and (HRNet) the upsample adjoint are one
+    kernel (rhseg_head_dz_*_fused), so no gradient tensor exists at output resolution for HRNet,
+  * nothing synchronises with the host: all scalars come back in one small device tensor.
+The drop-in modules (Models/, Metrics/) give the same numbers through the reference's own call
+sequence; this is the additive fast path ("fused step").
+"""
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import native
+from .head import alloc_weight_sums, forward_levels, level_weight_backward
+from .native import call, ptr, stream_of
+from .tree_tables import ClassTree
+
+_I32 = ctypes.c_int32
+
+
+class StepOutput:
+    """Everything one training step reports, still on the device (no host sync)."""
+    __slots__ = ("loss", "scalars", "level_ce", "level_dice", "consistency", "confusion", "ratios", "probs", "logits")
+
+    def __init__(self, loss, scalars, confusion, ratios, probs, logits, n):
+        self.loss = loss                       # 0-dim, differentiable
+        self.scalars = scalars                 # [2 + 4*n] fp32: total, consistency, then (ce, dice, n_dice, n_ce) per level
+        self.consistency = scalars[1]
+        self.level_ce = [scalars[2 + 4 * L] for L in range(n)]
+        self.level_dice = [scalars[3 + 4 * L] for L in range(n)]
+        self.confusion = confusion             # per level int64 [nc,nc]
+        self.ratios = ratios                   # per level fp32 [5,nc] (rows: dice, iou, accuracy, precision, recall)
+        self.probs, self.logits = probs, logits
+
+
+def _eval_layout(tree: ClassTree, B: int):
+    """Word offsets (8-byte words) of each level's [stats | consistency sums | confusion] block."""
+    offs, off = [], 0
+    for L, K in enumerate(tree.head_channels):
+        nc = K + 1 if L > 0 else K
+        offs.append((off, off + B * K * native.NSTAT, off + B * K * native.NSTAT + native.MAX_K, nc))
+        off += B * K * native.NSTAT + native.MAX_K + nc * nc
+    return offs, off
+
+
+class _FusedStepFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tree: ClassTree, out_size, weights_all, smooth, target, *tensors):
+        n = tree.num_levels
+        r = forward_levels(tree, out_size, tensors)
+        B, C, Hf, Wf, H, W = r["dims"]
+        dev = r["feats"][0].device
+        st = stream_of(r["feats"][0])
+        tables = tree.device_tables(dev)
+        n_pix = H * W
+        native.require_cuda(target)
+        if target.dtype != torch.float32:
+            target = target.float()
+        if target.dim() != 4 or target.shape[0] != B or target.shape[1] != sum(tree.head_channels) \
+                or tuple(target.shape[2:]) != (H, W):
+            raise native.NativeError("target must be [B, sum(K_L), H, W] = [%d,%d,%d,%d], got %s"
+                                     % (B, sum(tree.head_channels), H, W, tuple(target.shape)))
+        if not (target.stride(3) == 1 and target.stride(2) == W):
+            target = target.contiguous()
+        t_bs, t_cs = target.stride(0), target.stride(1)
+        # ---- evaluation: one pass per level ----
+        offs, words = _eval_layout(tree, B)
+        ws = torch.empty((words,), dtype=torch.float64, device=dev)
+        idx_maps = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) if L < n - 1 else None for L in range(n)]
+        ch_off = [0]
+        for k in tree.head_channels:
+            ch_off.append(ch_off[-1] + k)
+        esz = target.element_size()
+        for L in range(n):
+            K = tree.head_channels[L]
+            t_ptr = target.data_ptr() + ch_off[L] * t_cs * esz
+            pt_ptr = target.data_ptr() + ch_off[L - 1] * t_cs * esz if L > 0 else None
+            call("rhseg_level_eval", ptr(r["logits"][L]), t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs,
+                 ptr(idx_maps[L - 1]) if L > 0 else None, ptr(tables[L]), B, K, n_pix, 1 if L > 0 else 0,
+                 ws.data_ptr() + offs[L][0] * 8, ptr(idx_maps[L]), st)
+        scalars = torch.empty((2 + 4 * n,), dtype=torch.float32, device=dev)
+        coef_all = torch.empty((B * sum(tree.head_channels) * 3,), dtype=torch.float32, device=dev)
+        Ks = (_I32 * n)(*tree.head_channels)
+        Gs = (_I32 * n)(*[tree.group_count(L) for L in range(n)])
+        call("rhseg_step_finalize", ptr(ws), ptr(weights_all), B, n, Ks, Gs, float(smooth), n_pix, ptr(scalars),
+             ptr(coef_all), st)
+        conf, ratios = [], []
+        for L in range(n):
+            nc = offs[L][3]
+            c = ws[offs[L][2]:offs[L][2] + nc * nc].view(torch.int64).view(nc, nc)
+            rt = torch.empty((5, nc), dtype=torch.float32, device=dev)
+            call("rhseg_metric_ratios", ptr(c), nc, ptr(rt), st)
+            conf.append(c); ratios.append(rt)
+        ctx.tree, ctx.dims, ctx.upsampled = tree, r["dims"], r["upsampled"]
+        ctx.t_meta = (t_bs, t_cs, ch_off, esz)
+        ctx.save_for_backward(target, coef_all, *r["feats"], *r["head_w"], *r["film_w"], *r["logits"], *r["probs"],
+                              *r["psums"], *r["eff_ws"], *[g for g in r["gbs"] if g is not None])
+        ctx.set_materialize_grads(False)
+        outs = (scalars[0], scalars) + tuple(conf) + tuple(ratios) + tuple(r["probs"]) + tuple(r["logits"])
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_total, *_unused):
+        tree = ctx.tree
+        n = tree.num_levels
+        B, C, Hf, Wf, H, W = ctx.dims
+        sv = ctx.saved_tensors
+        target, coef_all = sv[0], sv[1]
+        sv = sv[2:]
+        feats, head_w, film_w = sv[0:n], sv[n:2 * n], sv[2 * n:3 * n - 1]
+        o = 3 * n - 1
+        logits, probs, psums, eff_ws = sv[o:o + n], sv[o + n:o + 2 * n], sv[o + 2 * n:o + 3 * n], sv[o + 3 * n:o + 4 * n]
+        gbs = [None] + list(sv[o + 4 * n:o + 5 * n - 1])
+        t_bs, t_cs, ch_off, esz = ctx.t_meta
+        n_grads = 5 * n - 2
+        if g_total is None:
+            return (None,) * (5 + n_grads)
+        dev = feats[0].device
+        st = stream_of(feats[0])
+        tables = tree.device_tables(dev)
+        n_pix = H * W
+        g = g_total.reshape(1)
+        g = g if g.dtype == torch.float32 else g.float()
+        sums = alloc_weight_sums(tree, B, C, dev)
+        d_feats: List[Optional[torch.Tensor]] = [None] * n
+        d_hw: List[Optional[torch.Tensor]] = [None] * n
+        d_hb: List[Optional[torch.Tensor]] = [None] * n
+        d_fw: List[Optional[torch.Tensor]] = [None] * (n - 1)
+        d_fb: List[Optional[torch.Tensor]] = [None] * (n - 1)
+        g_uniform, dp_pix, pix_mask = None, None, 0
+        coef_off = 0
+        coef_offs = []
+        for k in tree.head_channels:
+            coef_offs.append(coef_off)
+            coef_off += B * k * 3
+        for L in range(n - 1, -1, -1):
+            K = tree.head_channels[L]
+            K_prev = tree.head_channels[L - 1] if L > 0 else 0
+            mode = tree.act_mode[L]
+            dp_prev, prev_mask = None, 0
+            if mode == native.ACT_GROUPED and (g_uniform is not None or dp_pix is not None):
+                dp_prev = torch.zeros((B, K_prev, H, W), dtype=torch.float32, device=dev)
+                for pname, _ in tree.child_groups[L - 1]:
+                    prev_mask |= 1 << tree.levels[L - 1].index(pname)
+            t_ptr = target.data_ptr() + ch_off[L] * t_cs * esz
+            c_ptr = coef_all.data_ptr() + coef_offs[L] * 4
+            if ctx.upsampled:
+                dz = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev)
+                call("rhseg_head_dz_lowres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, ptr(g), ptr(g),
+                     ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]), ptr(g_uniform), 1.0 / n_pix, ptr(dp_pix),
+                     pix_mask, B, K, K_prev, Hf, Wf, H, W, mode, ptr(dz), ptr(dp_prev), st)
+            else:
+                dz = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
+                call("rhseg_head_dz_fullres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, ptr(g), ptr(g),
+                     ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]), ptr(g_uniform), 1.0 / n_pix, ptr(dp_pix),
+                     pix_mask, B, K, K_prev, n_pix, mode, ptr(dz), ptr(dp_prev), st)
+            S, s = sums[L]
+            d_feats[L], d_hw[L], d_hb[L], fw_g, fb_g, g_prev = level_weight_backward(
+                tree, L, ctx.dims, feats[L], dz, eff_ws[L], head_w[L], film_w[L - 1] if L > 0 else None, gbs[L],
+                psums[L - 1] if L > 0 else None, S, s, ctx.needs_input_grad[5 + L], st)
+            if L > 0:
+                d_fw[L - 1], d_fb[L - 1] = fw_g, fb_g
+            g_uniform, dp_pix, pix_mask = g_prev, dp_prev, prev_mask
+        return (None,) * 5 + tuple(d_feats) + tuple(d_hw) + tuple(d_hb) + tuple(d_fw) + tuple(d_fb)
+
+
+class FusedHierStep:
+    """Callable fused training step for one class tree and one set of per-level class weights.
+
+        step = FusedHierStep(tree_dict, level_weights)
+        out = step(feats, head_w, head_b, film_w, film_b, target, out_size=None)
+        out.loss.backward()            # or torch.autograd.grad(out.loss, ...)
+
+    `target` is the wide ternary tensor [B, sum(K_L), H, W] of the dataset (train.py:181-193).
+    """
+
+    def __init__(self, hierarchy, level_weights: Sequence[Sequence[float]], smooth: float = 0.0):
+        self.tree = hierarchy if isinstance(hierarchy, ClassTree) else ClassTree(hierarchy)
+        if len(level_weights) != self.tree.num_levels:
+            raise ValueError("level_weights needs one list per level")
+        for L, w in enumerate(level_weights):
+            if len(w) != self.tree.head_channels[L]:
+                raise ValueError("level %d has %d classes but %d weights" % (L, self.tree.head_channels[L], len(w)))
+        self._weights_host = [float(x) for w in level_weights for x in w]
+        self._weights = {}
+        self.smooth = float(smooth)
+        if self.tree.num_levels > 8:
+            raise native.NativeError("fused step supports trees up to 8 levels deep")
+
+    def weights(self, device):
+        key = str(device)
+        if key not in self._weights:
+            self._weights[key] = torch.tensor(self._weights_host, dtype=torch.float32).to(device)
+        return self._weights[key]
+
+    def __call__(self, feats, head_w, head_b, film_w, film_b, target, out_size: Optional[Tuple[int, int]] = None) -> StepOutput:
+        n = self.tree.num_levels
+        if not (len(feats) == len(head_w) == len(head_b) == n and len(film_w) == len(film_b) == n - 1):
+            raise native.NativeError("expected %d levels of features/heads and %d FiLMs" % (n, n - 1))
+        outs = _FusedStepFn.apply(self.tree, out_size, self.weights(feats[0].device), self.smooth, target,
+                                  *feats, *head_w, *head_b, *film_w, *film_b)
+        return StepOutput(outs[0], outs[1], list(outs[2:2 + n]), list(outs[2 + n:2 + 2 * n]),
+                          list(outs[2 + 2 * n:2 + 3 * n]), list(outs[2 + 3 * n:2 + 4 * n]), n)

@@ -24,53 +24,100 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def forward_levels(tree: ClassTree, out_size, tensors):
+    """Runs the per-level forward kernels.  `tensors` = feats[n] + head_w[n] + head_b[n] + film_w[n-1] +
+    film_b[n-1].  Returns a dict with the inputs (contiguous fp32) and probs / logits / psums / eff_w /
+    gamma_beta per level plus the shape tuple."""
+    n = tree.num_levels
+    feats = [_f32c(t) for t in tensors[0:n]]
+    head_w = [_f32c(t) for t in tensors[n:2 * n]]
+    head_b = [_f32c(t) for t in tensors[2 * n:3 * n]]
+    film_w = [_f32c(t) for t in tensors[3 * n:4 * n - 1]]
+    film_b = [_f32c(t) for t in tensors[4 * n - 1:5 * n - 2]]
+    native.require_cuda(*feats, *head_w, *head_b, *film_w, *film_b)
+    dev = feats[0].device
+    st = stream_of(feats[0])
+    tables = tree.device_tables(dev)
+    B, C, Hf, Wf = feats[0].shape
+    H, W = (Hf, Wf) if out_size is None else (int(out_size[0]), int(out_size[1]))
+    upsampled = (H, W) != (Hf, Wf)
+    n_pix = H * W
+    probs, logits, psums, eff_ws, gbs = [], [], [], [], []
+    # every level's fp64 pool sums live in one buffer zeroed by a single fill
+    psum_all = torch.zeros((sum(tree.head_channels) * B,), dtype=torch.float64, device=dev)
+    psum_off = 0
+    for L in range(n):
+        K = tree.head_channels[L]
+        K_prev = tree.head_channels[L - 1] if L > 0 else 0
+        f = feats[L]
+        if tuple(f.shape) != (B, C, Hf, Wf):
+            raise native.NativeError("per-level feature tensors must share one shape")
+        if tuple(head_w[L].shape[:2]) != (K, C):
+            raise native.NativeError("head weight of level %d has shape %s, expected [%d,%d,1,1]"
+                                     % (L, tuple(head_w[L].shape), K, C))
+        eff_w = torch.empty((B, K, C), dtype=torch.float32, device=dev)
+        eff_b = torch.empty((B, K), dtype=torch.float32, device=dev)
+        gb = torch.empty((B, 2 * C), dtype=torch.float32, device=dev) if L > 0 else None
+        call("rhseg_film_fold", ptr(head_w[L]), ptr(head_b[L]),
+             ptr(film_w[L - 1]) if L > 0 else None, ptr(film_b[L - 1]) if L > 0 else None,
+             ptr(psums[L - 1]) if L > 0 else None, float(n_pix), B, C, K, K_prev,
+             ptr(gb), ptr(eff_w), ptr(eff_b), st)
+        z = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
+        p = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
+        psum = psum_all[psum_off:psum_off + B * K].view(B, K)
+        psum_off += B * K
+        z_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev) if upsampled else None
+        call("rhseg_head_level_fwd", ptr(f), ptr(eff_w), ptr(eff_b),
+             ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
+             B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum), 0, st)
+        probs.append(p); logits.append(z); psums.append(psum); eff_ws.append(eff_w); gbs.append(gb)
+    return dict(feats=feats, head_w=head_w, head_b=head_b, film_w=film_w, film_b=film_b, probs=probs, logits=logits,
+                psums=psums, eff_ws=eff_ws, gbs=gbs, dims=(B, C, Hf, Wf, H, W), upsampled=upsampled)
+
+
+def level_weight_backward(tree, L, dims, feats_L, dz_feat, eff_w_L, head_w_L, film_w_prev, gb_L, psum_prev, S, s,
+                          want_dfeats, st):
+    """conv backward + parameter gradients of one level given dz at feature resolution.
+    Returns (d_feats or None, d_head_w, d_head_b, d_film_w or None, d_film_b or None, g_prev or None)."""
+    B, C, Hf, Wf, H, W = dims
+    K = tree.head_channels[L]
+    K_prev = tree.head_channels[L - 1] if L > 0 else 0
+    dev = feats_L.device
+    d_feats = torch.empty_like(feats_L) if want_dfeats else None
+    call("rhseg_head_conv_bwd", ptr(feats_L), ptr(dz_feat), ptr(eff_w_L), B, C, K, Hf * Wf,
+         ptr(d_feats), ptr(S), ptr(s), 0, st)
+    d_hw = torch.empty_like(head_w_L)
+    d_hb = torch.empty((K,), dtype=torch.float32, device=dev)
+    d_fw = d_fb = g_prev = None
+    if L > 0:
+        d_fw = torch.empty_like(film_w_prev)
+        d_fb = torch.empty((2 * C,), dtype=torch.float32, device=dev)
+        g_prev = torch.empty((B, K_prev), dtype=torch.float64, device=dev)
+    call("rhseg_head_param_grads", ptr(S), ptr(s), ptr(head_w_L), ptr(film_w_prev) if L > 0 else None, ptr(gb_L),
+         ptr(psum_prev) if L > 0 else None, float(H * W), B, C, K, K_prev, ptr(d_hw), ptr(d_hb),
+         ptr(d_fw), ptr(d_fb), ptr(g_prev), st)
+    return d_feats, d_hw, d_hb, d_fw, d_fb, g_prev
+
+
+def alloc_weight_sums(tree, B, C, dev):
+    """One zero-filled fp64 buffer holding S [B,K,C] and s [B,K] of every level; returns per-level views."""
+    total = sum(B * k * (C + 1) for k in tree.head_channels)
+    buf = torch.zeros((total,), dtype=torch.float64, device=dev)
+    views, off = [], 0
+    for k in tree.head_channels:
+        views.append((buf[off:off + B * k * C].view(B, k, C), buf[off + B * k * C:off + B * k * (C + 1)].view(B, k)))
+        off += B * k * (C + 1)
+    return views
+
+
 class _HierHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tree: ClassTree, out_size: Optional[Tuple[int, int]], *tensors):
         n = tree.num_levels
-        feats = [_f32c(t) for t in tensors[0:n]]
-        head_w = [_f32c(t) for t in tensors[n:2 * n]]
-        head_b = [_f32c(t) for t in tensors[2 * n:3 * n]]
-        film_w = [_f32c(t) for t in tensors[3 * n:4 * n - 1]]
-        film_b = [_f32c(t) for t in tensors[4 * n - 1:5 * n - 2]]
-        native.require_cuda(*feats, *head_w, *head_b, *film_w, *film_b)
-        dev = feats[0].device
-        st = stream_of(feats[0])
-        tables = tree.device_tables(dev)
-        B, C, Hf, Wf = feats[0].shape
-        H, W = (Hf, Wf) if out_size is None else (int(out_size[0]), int(out_size[1]))
-        upsampled = (H, W) != (Hf, Wf)
-        n_pix = H * W
-        probs, logits, psums, eff_ws, gbs = [], [], [], [], []
-        # every level's fp64 pool sums live in one buffer zeroed by a single fill
-        psum_all = torch.zeros((sum(tree.head_channels) * B,), dtype=torch.float64, device=dev)
-        psum_off = 0
-        for L in range(n):
-            K = tree.head_channels[L]
-            K_prev = tree.head_channels[L - 1] if L > 0 else 0
-            f = feats[L]
-            if tuple(f.shape) != (B, C, Hf, Wf):
-                raise native.NativeError("per-level feature tensors must share one shape")
-            if tuple(head_w[L].shape[:2]) != (K, C):
-                raise native.NativeError("head weight of level %d has shape %s, expected [%d,%d,1,1]"
-                                         % (L, tuple(head_w[L].shape), K, C))
-            eff_w = torch.empty((B, K, C), dtype=torch.float32, device=dev)
-            eff_b = torch.empty((B, K), dtype=torch.float32, device=dev)
-            gb = torch.empty((B, 2 * C), dtype=torch.float32, device=dev) if L > 0 else None
-            call("rhseg_film_fold", ptr(head_w[L]), ptr(head_b[L]),
-                 ptr(film_w[L - 1]) if L > 0 else None, ptr(film_b[L - 1]) if L > 0 else None,
-                 ptr(psums[L - 1]) if L > 0 else None, float(n_pix), B, C, K, K_prev,
-                 ptr(gb), ptr(eff_w), ptr(eff_b), st)
-            z = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
-            p = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
-            psum = psum_all[psum_off:psum_off + B * K].view(B, K)
-            psum_off += B * K
-            z_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev) if upsampled else None
-            call("rhseg_head_level_fwd", ptr(f), ptr(eff_w), ptr(eff_b),
-                 ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
-                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum), 0, st)
-            probs.append(p); logits.append(z); psums.append(psum); eff_ws.append(eff_w); gbs.append(gb)
-        ctx.tree, ctx.dims, ctx.upsampled = tree, (B, C, Hf, Wf, H, W), upsampled
+        r = forward_levels(tree, out_size, tensors)
+        feats, head_w, film_w = r["feats"], r["head_w"], r["film_w"]
+        probs, logits, psums, eff_ws, gbs = r["probs"], r["logits"], r["psums"], r["eff_ws"], r["gbs"]
+        ctx.tree, ctx.dims, ctx.upsampled = tree, r["dims"], r["upsampled"]
         ctx.save_for_backward(*feats, *head_w, *film_w, *logits, *probs, *psums, *eff_ws, *[g for g in gbs if g is not None])
         ctx.set_materialize_grads(False)
         outs = tuple(probs) + tuple(logits)
@@ -98,9 +145,7 @@ class _HierHeadFn(torch.autograd.Function):
         d_fw: List[Optional[torch.Tensor]] = [None] * (n - 1)
         d_fb: List[Optional[torch.Tensor]] = [None] * (n - 1)
 
-        # all fp64 weight-gradient sums (S [B,K,C] and s [B,K] per level) in one zero-filled buffer
-        sums_all = torch.zeros((sum(B * k * (C + 1) for k in tree.head_channels),), dtype=torch.float64, device=dev)
-        sums_off = 0
+        sums = alloc_weight_sums(tree, B, C, dev)
         g_uniform = None   # [B,K_L] fp64: dLoss/d(sum_n P_L) * n_pix, from level L+1's FiLM
         dp_pix = None      # [B,K_L,H,W]: per-pixel dLoss/dP_L (composition of level L+1 and/or user grads)
         pix_mask = 0
@@ -134,26 +179,14 @@ class _HierHeadFn(torch.autograd.Function):
                 continue  # nothing reaches this level's logits: no gradient for its features / parameters
             if ctx.upsampled:
                 dz_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev)
-                call("rhseg_upsample_adjoint", ptr(dz), B * K, Hf, Wf, H, W, ptr(dz_lo), st)
+                call("rhseg_upsample_adjoint", ptr(dz), B, K, Hf, Wf, H, W, ptr(dz_lo), st)
                 dz = dz_lo
-            S = sums_all[sums_off:sums_off + B * K * C].view(B, K, C)
-            s = sums_all[sums_off + B * K * C:sums_off + B * K * (C + 1)].view(B, K)
-            sums_off += B * K * (C + 1)
-            if ctx.needs_input_grad[2 + L]:
-                d_feats[L] = torch.empty_like(feats[L])
-            call("rhseg_head_conv_bwd", ptr(feats[L]), ptr(dz), ptr(eff_ws[L]), B, C, K, n_feat,
-                 ptr(d_feats[L]), ptr(S), ptr(s), 0, st)
-            d_hw[L] = torch.empty_like(head_w[L])
-            d_hb[L] = torch.empty((K,), dtype=torch.float32, device=dev)
-            g_prev = None
+            S, s = sums[L]
+            d_feats[L], d_hw[L], d_hb[L], fw_g, fb_g, g_prev = level_weight_backward(
+                tree, L, ctx.dims, feats[L], dz, eff_ws[L], head_w[L], film_w[L - 1] if L > 0 else None, gbs[L],
+                psums[L - 1] if L > 0 else None, S, s, ctx.needs_input_grad[2 + L], st)
             if L > 0:
-                d_fw[L - 1] = torch.empty_like(film_w[L - 1])
-                d_fb[L - 1] = torch.empty((2 * C,), dtype=torch.float32, device=dev)
-                g_prev = torch.empty((B, K_prev), dtype=torch.float64, device=dev)
-            call("rhseg_head_param_grads", ptr(S), ptr(s), ptr(head_w[L]),
-                 ptr(film_w[L - 1]) if L > 0 else None, ptr(gbs[L]), ptr(psums[L - 1]) if L > 0 else None,
-                 float(n_pix), B, C, K, K_prev, ptr(d_hw[L]), ptr(d_hb[L]),
-                 ptr(d_fw[L - 1]) if L > 0 else None, ptr(d_fb[L - 1]) if L > 0 else None, ptr(g_prev), st)
+                d_fw[L - 1], d_fb[L - 1] = fw_g, fb_g
             g_uniform = g_prev
         return (None, None) + tuple(d_feats) + tuple(d_hw) + tuple(d_hb) + tuple(d_fw) + tuple(d_fb)
 

@@ -29,7 +29,8 @@ SIGNATURES = {
     "rhseg_film_fold": [_P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _P, _P, _P, _P],
     "rhseg_head_level_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P],
     "rhseg_head_act_bwd": [_P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _I, _P, _P, _P],
-    "rhseg_upsample_adjoint": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "rhseg_upsample_adjoint": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "rhseg_head_dz_lowres_fused": [_P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "rhseg_head_conv_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "rhseg_head_param_grads": [_P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "rhseg_loss_stats": [_P, _P, _L, _L, _I, _I, _I, _I, _P, _P],
@@ -39,6 +40,9 @@ SIGNATURES = {
     "rhseg_confusion_matrix": [_P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P, _P],
     "rhseg_metric_ratios": [_P, _I, _P, _P],
     "rhseg_predict_onehot": [_P, _P, _L, _L, _I, _I, _I, _P, _P, _P, _P],
+    "rhseg_head_dz_fullres_fused": [_P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _P, _P, _P],
+    "rhseg_step_finalize": [_P, _P, _I, _I, _P, _P, _D, _L, _P, _P, _P],
+    "rhseg_level_eval": [_P, _P, _L, _L, _P, _L, _L, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "rhseg_confusion_from_logits": [_P, _P, _L, _L, _I, _I, _I, _I, _P, _P],
 }
 

@@ -1,0 +1,127 @@
+"""GPU parity of the fused training step (rhseg_b200.FusedHierStep): same inputs as the
+reference-generated fixtures, compared with the reference's recorded outputs (loss, gradients)
+and with the oracle (metrics, consistency)."""
+import math
+
+import pytest
+import torch
+
+from helpers import HIER_CASES, Fixture, close
+from oracle import hier_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _step(fx, requires_grad=True):
+    import rhseg_b200
+    step = rhseg_b200.FusedHierStep(fx.tree, fx.level_weights)
+    mk = lambda ts: [t.to(DEV).requires_grad_(requires_grad) for t in ts]
+    feats = mk(fx.per_level("feats"))
+    hw, hb = mk(fx.per_level("head_w")), mk(fx.per_level("head_b"))
+    fw, fb = mk(fx.per_level("film_w", n=fx.nL - 1)), mk(fx.per_level("film_b", n=fx.nL - 1))
+    # the wide target tensor sits inside a larger buffer so that level slices are strided views
+    tcat = torch.cat(fx.per_level("target"), dim=1)
+    wide = torch.zeros(tcat.shape[0], tcat.shape[1] + 3, *tcat.shape[2:])
+    wide[:, 1:1 + tcat.shape[1]] = tcat
+    target = wide.to(DEV)[:, 1:1 + tcat.shape[1]]
+    out = step(feats, hw, hb, fw, fb, target, fx.out_size)
+    return step, out, (feats, hw, hb, fw, fb)
+
+
+@pytest.mark.parametrize("name", HIER_CASES)
+def test_fused_step_matches_reference(name):
+    fx = Fixture(name)
+    step, out, (feats, hw, hb, fw, fb) = _step(fx)
+    ref_total = fx.f("total_loss")
+    assert abs(out.loss.item() - ref_total) <= 1e-5 * abs(ref_total), (out.loss.item(), ref_total)
+    assert abs(out.consistency.item() - fx.f("consistency_train")) <= 1e-6
+    levels, parent_of, _, groups = O.hierarchy_tables(fx.tree)
+    for L in range(fx.nL):
+        assert abs(out.level_ce[L].item() - fx.f(f"ce{L}")) <= 1e-5 * max(1.0, abs(fx.f(f"ce{L}")))
+        if math.isnan(fx.f(f"dice{L}")):
+            assert out.level_dice[L].item() == 0.0 and out.scalars[4 + 4 * L].item() == 0.0
+        else:
+            assert abs(out.level_dice[L].item() - fx.f(f"dice{L}")) <= 1e-5
+        close(out.logits[L], fx.t(f"logits{L}"), what=f"{name} logits{L}")
+        close(out.probs[L], fx.t(f"probs{L}"), what=f"{name} probs{L}")
+        # metrics: the reference's glue (masked one-hot vs eval target) through the oracle's restated torchmetrics
+        onehot = fx.t(f"onehot{L}")
+        eval_t = torch.where(fx.t(f"target{L}") == -1, 0, fx.t(f"target{L}"))
+        want = O.level_confusion(onehot, eval_t, onehot.shape[1], L != 0)
+        assert torch.equal(out.confusion[L].cpu(), want), f"{name} confusion{L}"
+        r = O.ratios_from_confusion(want)
+        for row, key in enumerate(("dice", "iou", "accuracy", "precision", "recall")):
+            assert torch.equal(out.ratios[L][row].cpu(), r[key]), (name, L, key)
+    out.loss.backward()
+    for L in range(fx.nL):
+        close(feats[L].grad, fx.t(f"dfeats{L}"), what=f"{name} dfeats{L}")
+        close(hw[L].grad, fx.t(f"dhead_w{L}"), what=f"{name} dhead_w{L}")
+        close(hb[L].grad, fx.t(f"dhead_b{L}"), what=f"{name} dhead_b{L}")
+    for i in range(fx.nL - 1):
+        close(fw[i].grad, fx.t(f"dfilm_w{i}"), what=f"{name} dfilm_w{i}")
+        close(fb[i].grad, fx.t(f"dfilm_b{i}"), what=f"{name} dfilm_b{i}")
+
+
+@pytest.mark.parametrize("name", ["unet_ext", "hrnet_ext", "hrnet_tl"])
+def test_fused_step_equals_dropin_modules(name):
+    """The fused node and the drop-in module sequence are two routes to the same numbers."""
+    import rhseg_b200
+    from rhseg_b200 import metric_ops
+    from rhseg_b200.Metrics import losses
+    fx = Fixture(name)
+    _, out, leaves_a = _step(fx)
+    out.loss.backward()
+    tree = rhseg_b200.ClassTree(fx.tree)
+    mk = lambda ts: [t.to(DEV).requires_grad_(True) for t in ts]
+    feats = mk(fx.per_level("feats"))
+    hw, hb = mk(fx.per_level("head_w")), mk(fx.per_level("head_b"))
+    fw, fb = mk(fx.per_level("film_w", n=fx.nL - 1)), mk(fx.per_level("film_b", n=fx.nL - 1))
+    probs, logits = rhseg_b200.hier_head_forward(tree, feats, hw, hb, fw, fb, fx.out_size)
+    targets = [t.to(DEV) for t in fx.per_level("target")]
+    total, onehots = 0.0, []
+    for L in range(fx.nL):
+        onehot, eval_t = metric_ops.predict_onehot(logits[L].detach(), targets[L])
+        onehots.append(onehot)
+        assert torch.equal(metric_ops.confusion_matrix(onehot, eval_t, L != 0), out.confusion[L])
+        total = total + losses.CrossEntropyLoss()(logits[L], targets[L], True, fx.level_weights[L])
+        d = losses.SoftDiceLoss()(logits[L], targets[L], True, fx.level_weights[L])
+        total = total + (d if d is not None else 0.0)
+    total = total + losses.hierarchical_consistency_loss(onehots, tree.levels, tree.parent_of)
+    total.backward()
+    assert abs(total.item() - out.loss.item()) <= 2e-6 * abs(total.item())
+    for a, b in zip(leaves_a, (feats, hw, hb, fw, fb)):
+        for x, y in zip(a, b):
+            close(x.grad, y.grad, rtol=2e-6, what=name)
+
+
+def test_fused_step_full_size_hrnet_against_oracle_sample():
+    """BASELINE.json configs[1] shape (HRNet-W48 tl, 620x620): one sample against the oracle on CPU."""
+    import rhseg_b200
+    import bench
+    wl = dict(bench.WORKLOADS["hrnet_w48_tl_620_b4"])
+    data = bench.synth_inputs(wl, 1, seed=3, device="cpu")
+    h = data["host"]
+    leaves_ref = [[t.clone().requires_grad_(True) for t in h[k]] for k in ("feats", "hw", "hb", "fw", "fb")]
+    levels, parent_of, groups = data["levels"], data["parent_of"], data["groups"]
+    probs, logits = O.head_forward(*leaves_ref, levels, groups, (620, 620))
+    targets, s = [], 0
+    for k in data["chans"]:
+        targets.append(h["target"][:, s:s + k]); s += k
+    onehots, eval_t = O.predict_onehot_masked([z.detach() for z in logits], targets)
+    loss_ref, _ = O.total_loss(logits, targets, data["weights"], onehots, levels, parent_of)
+    loss_ref.backward()
+    step = rhseg_b200.FusedHierStep(wl["tree"], data["weights"])
+    leaves = [[t.clone().to(DEV).requires_grad_(True) for t in h[k]] for k in ("feats", "hw", "hb", "fw", "fb")]
+    out = step(*leaves, h["target"].to(DEV), (620, 620))
+    out.loss.backward()
+    assert abs(out.loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    for L in range(2):
+        # argmax-derived integers: compare on the device's own logits (the conv reduction order differs
+        # from ATen's by ~1e-7, which may flip exact near-ties)
+        oh_dev, et_dev = O.predict_onehot_masked([out.logits[L].cpu()], [targets[L]])
+        assert torch.equal(out.confusion[L].cpu(), O.level_confusion(oh_dev[0], et_dev[0], 4, L != 0))
+        close(out.logits[L], logits[L], what=f"logits{L}")
+        close(leaves[0][L].grad, leaves_ref[0][L].grad, what=f"dfeats{L}")
+        close(leaves[1][L].grad, leaves_ref[1][L].grad, rtol=2e-5, what=f"dhead_w{L}")
+    close(leaves[3][0].grad, leaves_ref[3][0].grad, rtol=2e-5, what="dfilm_w0")
