@@ -112,6 +112,7 @@ class GpuStep:
         self.target = h["target"].to(device)
         self.out_size = None if wl["scale"] == 1 else (wl["H"], wl["W"])
         self.ce, self.dice = losses.CrossEntropyLoss(), losses.SoftDiceLoss()
+        self.fused = rhseg_b200.FusedHierStep(self.tree, data["weights"])
         self.result = None
 
     def targets(self):
@@ -122,6 +123,16 @@ class GpuStep:
         return out
 
     def step(self):
+        """Fused step (rhseg_b200.FusedHierStep): the whole train_epoch body in one autograd node."""
+        hw, hb, fw, fb = self.params
+        out = self.fused(self.feats, hw, hb, fw, fb, self.target, self.out_size)
+        leaves = self.feats + [p for grp in self.params for p in grp]
+        self.grads = torch.autograd.grad(out.loss, leaves)  # dfeats per level + head / FiLM parameter grads
+        self.result = (out.scalars, out.ratios)
+        return self.result
+
+    def step_dropin(self):
+        """Same work through the drop-in modules, called the way train.py calls them."""
         self.rh.clear_memo()
         hw, hb, fw, fb = self.params
         probs, logits = self.rh.hier_head_forward(self.tree, self.feats, hw, hb, fw, fb, self.out_size)
@@ -139,9 +150,8 @@ class GpuStep:
             loss = ce + di if loss is None else loss + ce + di
         loss = loss + self.losses.hierarchical_consistency_loss(onehots, self.tree.levels, self.tree.parent_of)
         leaves = self.feats + [p for grp in self.params for p in grp]
-        self.grads = torch.autograd.grad(loss, leaves)  # dfeats per level + head / FiLM parameter grads
-        self.result = (loss.detach(), ratios)
-        return self.result
+        grads = torch.autograd.grad(loss, leaves)
+        return loss.detach(), ratios, grads
 
 
 class ClockSampler:
@@ -225,10 +235,11 @@ def run_ours(args, rank, world, local_rank):
         else:
             raw_call(name, *a)
 
+    import rhseg_b200.fused as fused_mod
     import rhseg_b200.head as head_mod
     import rhseg_b200.loss_ops as loss_mod
     import rhseg_b200.metric_ops as met_mod
-    for mod in (native, head_mod, loss_mod, met_mod):
+    for mod in (native, head_mod, loss_mod, met_mod, fused_mod):
         mod.call = counting_call
 
     def barrier():
@@ -241,8 +252,8 @@ def run_ours(args, rank, world, local_rank):
         head/FiLM parameter gradients (tiny; pixel data never leaves its GPU)."""
         if world == 1:
             return
-        loss, ratios = result
-        parts = [loss.reshape(1).double()] + [r.flatten().double() for r in ratios]
+        scal, ratios = result
+        parts = [scal.reshape(-1).double()] + [r.flatten().double() for r in ratios]
         parts += [g.flatten().double() for g in st.grads[len(st.feats):]]
         buf = torch.cat(parts)
         torch.distributed.all_reduce(buf)
@@ -300,6 +311,18 @@ def run_ours(args, rank, world, local_rank):
         launches_per_step = counted["n"]
         torch.cuda.synchronize()
 
+    # ---- the same step through the drop-in modules (reference call sequence), eager ----
+    for _ in range(3):
+        st.step_dropin()
+    torch.cuda.synchronize()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(min(args.steps, 20)):
+        st.step_dropin()
+    d1.record()
+    torch.cuda.synchronize()
+    dropin_ms = d0.elapsed_time(d1) / min(args.steps, 20)
+
     # ---- dominant-kernel timing, live, on the launching stream (eager steps, inputs > L2) ----
     timing_on["v"] = True
     for _ in range(min(args.steps, 20)):
@@ -316,7 +339,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- end-to-end from pinned host buffers (`e2e`) ----
     host = data["host"]
     h2d = sum(f.numel() * 4 for f in host["feats"]) + host["target"].numel() * 4
-    out_host = torch.empty(1 + sum(5 * (k + (1 if L else 0)) for L, k in enumerate(data["chans"])), dtype=torch.float32).pin_memory()
+    out_host = torch.empty(2 + 4 * len(data["chans"]) + sum(5 * (k + (1 if L else 0)) for L, k in enumerate(data["chans"])),
+                           dtype=torch.float32).pin_memory()
     d2h = out_host.numel() * 4
 
     def e2e_step():
@@ -324,9 +348,9 @@ def run_ours(args, rank, world, local_rank):
             for dst, src in zip(st.feats, host["feats"]):
                 dst.copy_(src, non_blocking=True)
             st.target.copy_(host["target"], non_blocking=True)
-        loss, ratios = st.step()
-        exchange((loss, ratios))
-        out_host.copy_(torch.cat([loss.reshape(1)] + [r.flatten() for r in ratios]), non_blocking=True)
+        scal, ratios = st.step()
+        exchange((scal, ratios))
+        out_host.copy_(torch.cat([scal] + [r.flatten() for r in ratios]), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads loss / metrics on the host every step
 
     for _ in range(2):
@@ -358,7 +382,7 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "tree_levels": data["chans"], "feat_channels": wl["C"],
                    "batch_per_gpu": B, "image": [wl["H"], wl["W"]], "feat_hw": list(feat_hw(wl)),
-                   "step": "head fwd + train-path prediction + 5 confusion metrics + CE/Dice/consistency + bwd (dfeats, head+FiLM grads)",
+                   "step": "head fwd + train-path prediction + 5 confusion metrics + CE/Dice/consistency + bwd (dfeats, head+FiLM grads); fused step API",
                    "l2_policy": "inputs larger than L2 (%.0f MB of features per step vs 126 MB L2)" % (sum(f.numel() * 4 for f in st.feats) / 1e6),
                    "cuda_graph": graph is not None, "collective": "1 all-reduce/step (loss+metrics+head grads)" if world > 1 else "none"},
         "step_bytes": {"algorithmic_head_loss_fwd_bwd": alg["step"], "metrics": alg["metrics"],
@@ -372,6 +396,8 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": world * px / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "note": "features+targets copied from pinned host memory every step; PCIe-bound"},
+        "dropin_modules": {"ms_per_step": dropin_ms, "value": px / (dropin_ms * 1e-3) / 1e6, "unit": "Mpixel/s",
+                           "note": "same step through Models/Metrics drop-in modules in the reference's call order, eager, this rank"},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
     }

@@ -231,7 +231,8 @@ int rhseg_head_dz_fullres_fused(const float* logits, const float* targets, long 
 /* All levels of one training step from the rhseg_level_eval workspaces (stored back to back in
  * level order), one launch:  out[0] = total = sum_L (CE_L + Dice_L) + consistency
  * (train.py:132-149), out[1] = consistency, out[2+4L .. 2+4L+3] = rhseg_loss_finalize's out4 of
- * level L; coef_all = the levels' [B,K_L,3] backward coefficients back to back.
+ * level L, followed by each level's [5,nc_L] ratio block of rhseg_metric_ratios computed from the
+ * workspace's confusion matrix; coef_all = the levels' [B,K_L,3] backward coefficients back to back.
  * weights_all = the levels' class weights back to back; K_per_level / groups_per_level are HOST
  * arrays (groups_per_level[0] is ignored).                                                  */
 int rhseg_step_finalize(const void* eval_words, const float* weights_all, int B, int n_levels,

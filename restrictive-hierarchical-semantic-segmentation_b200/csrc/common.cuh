@@ -153,7 +153,11 @@ struct LevelInfo {
   int parent[RHSEG_KERNEL_MAX_K];
 };
 
-__device__ __forceinline__ float sigmoidf_ref(float z) { return 1.0f / (1.0f + expf(-z)); }
+// Probability math uses the SFU approximations (ex2.approx / rcp with ~1-2 ulp error): the outputs
+// are compared with the reference at 1e-5 relative, three orders of magnitude above that error,
+// and the kernels that evaluate them are instruction-bound otherwise.  Anything that decides an
+// INTEGER result (argmax of softmax) goes through argmax_softmax_aten() below instead.
+__device__ __forceinline__ float sigmoidf_ref(float z) { return __frcp_rn(1.0f + __expf(-z)); }
 
 // Segmented (per contiguous group) softmax over K channels; groups start where start_mask has a bit.
 template <int K>
@@ -166,14 +170,19 @@ __device__ __forceinline__ void grouped_softmax(const float (&z)[K], int start_m
   for (int k = K - 2; k >= 0; --k) m[k] = ((start_mask >> (k + 1)) & 1) ? m[k] : m[k + 1];
   float e[K], s[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) e[k] = expf(z[k] - m[k]);
+  for (int k = 0; k < K; ++k) e[k] = __expf(z[k] - m[k]);
   s[0] = e[0];
 #pragma unroll
   for (int k = 1; k < K; ++k) s[k] = ((start_mask >> k) & 1) ? e[k] : s[k - 1] + e[k];
 #pragma unroll
   for (int k = K - 2; k >= 0; --k) s[k] = ((start_mask >> (k + 1)) & 1) ? s[k] : s[k + 1];
+  // one reciprocal per group (computed at the group's first channel, copied forward)
+  float r[K];
+  r[0] = __frcp_rn(s[0]);
 #pragma unroll
-  for (int k = 0; k < K; ++k) q[k] = e[k] / s[k];
+  for (int k = 1; k < K; ++k) r[k] = ((start_mask >> k) & 1) ? __frcp_rn(s[k]) : r[k - 1];
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = e[k] * r[k];
 }
 
 // Per-group sum broadcast back to every member: out[k] = sum_{j in group(k)} x[j].
@@ -199,6 +208,50 @@ __device__ __forceinline__ void full_softmax(const float (&z)[K], float (&p)[K],
   for (int k = 0; k < K; ++k) p[k] = p[k] / sum;
 }
 
+// softmax over all K channels with SFU math (statistics / gradients; see the note above)
+template <int K>
+__device__ __forceinline__ void fast_softmax(const float (&z)[K], float (&p)[K], float& mx, float& sum) {
+  mx = z[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) mx = fmaxf(mx, z[k]);
+  sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { p[k] = __expf(z[k] - mx); sum += p[k]; }
+  const float inv = __frcp_rn(sum);
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] *= inv;
+}
+
+// torch.argmax semantics: first maximum, NaN counts as the maximum.
+__device__ __forceinline__ bool beats(float v, float best) { return (v > best) || (v != v && best == best); }
+
+// torch.argmax(torch.softmax(z, 1), 1) of one pixel, bit-exact with ATen's float kernels.
+// softmax is monotone, so the answer is the first maximum of z unless rounding inside softmax
+// creates a tie with an EARLIER channel; that needs a logit within ~2.4e-7 of the maximum
+// (exp(-d) must round to 1 or 1-ulp).  Only such near-ties (and non-finite inputs) take the slow
+// path that replays ATen's arithmetic: max, sequential sum of expf(z-max), IEEE division.
+template <int K>
+__device__ __forceinline__ int argmax_softmax_aten(const float (&z)[K]) {
+  float best = z[0];
+  int idx = 0;
+#pragma unroll
+  for (int k = 1; k < K; ++k)
+    if (z[k] > best) { best = z[k]; idx = k; }
+  bool slow = !(fabsf(best) <= 3.0e38f);  // inf / NaN anywhere near the top
+#pragma unroll
+  for (int k = 0; k < K; ++k) slow |= (k != idx) && !(best - z[k] > 2.0e-6f);
+  if (slow) {
+    float p[K], mx, sum;
+    full_softmax<K>(z, p, mx, sum);
+    best = p[0];
+    idx = 0;
+#pragma unroll
+    for (int k = 1; k < K; ++k)
+      if (beats(p[k], best)) { best = p[k]; idx = k; }
+  }
+  return idx;
+}
+
 // ---- per-pixel gradient math shared by the stand-alone and the fused backward kernels ----
 
 // d(g_ce*CE + g_dice*Dice)/dz at one pixel from the closed-form coefficients
@@ -216,7 +269,7 @@ __device__ __forceinline__ void loss_dz_pixel(const float (&z)[K], const float (
   }
   if constexpr (LOGITS) {
     float p[K], mx, sum, sa = 0.f, sgp = 0.f;
-    full_softmax<K>(z, p, mx, sum);
+    fast_softmax<K>(z, p, mx, sum);
 #pragma unroll
     for (int k = 0; k < K; ++k) { sa += a[k]; sgp = fmaf(g[k], p[k], sgp); }
 #pragma unroll

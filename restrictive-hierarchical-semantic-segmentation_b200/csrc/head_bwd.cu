@@ -379,60 +379,98 @@ using BwdCfgS1 = PipeCfg<8, 8, 3>;  // scalar rows: T = 256*J px
 // ------------------------------------------------------------------------------------
 // parameter gradients (tiny): one thread per feature channel
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// Thread (cl, bl): channel blockIdx.x*PG_CH + cl, samples b = bl, bl+PG_BL, ...  All global loads of a
+// thread are independent (one sample per thread when B <= PG_BL), the sums over samples and over
+// channels go through shared memory.
+constexpr int PG_CH = 64, PG_BL = 4, PG_THREADS = PG_CH * PG_BL;
+
+__global__ void __launch_bounds__(PG_THREADS)
 param_grads_kernel(const double* __restrict__ S, const double* __restrict__ s, const float* __restrict__ head_w,
                    const float* __restrict__ film_w, const float* __restrict__ gamma_beta,
                    const double* __restrict__ prev_psum, double n_pix, int B, int C, int K, int K_prev,
                    float* __restrict__ d_head_w, float* __restrict__ d_head_b, float* __restrict__ d_film_w,
                    float* __restrict__ d_film_b, double* __restrict__ g_prev) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int NV = RHSEG_KERNEL_MAX_K + 2 + 2 * RHSEG_MAX_K;  // dw[k], dfb_g, dfb_b, dfw_g[j], dfw_b[j]
+  __shared__ float red[PG_BL][PG_CH][NV + 1];
+  __shared__ float gsm[PG_THREADS / 32];
+  const int cl = threadIdx.x % PG_CH, bl = threadIdx.x / PG_CH;
+  const int c = blockIdx.x * PG_CH + cl;
   const bool ok = c < C;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (blockIdx.x == 0 && threadIdx.x < K) {
     double acc = 0.0;
     for (int b = 0; b < B; ++b) acc += s[b * K + threadIdx.x];
     d_head_b[threadIdx.x] = (float)acc;
   }
-  double dw[RHSEG_KERNEL_MAX_K];
-  for (int k = 0; k < RHSEG_KERNEL_MAX_K; ++k) dw[k] = 0.0;
-  double dfw_g[RHSEG_MAX_K], dfw_b[RHSEG_MAX_K], dfb_g = 0.0, dfb_b = 0.0;
-  for (int j = 0; j < RHSEG_MAX_K; ++j) { dfw_g[j] = 0.0; dfw_b[j] = 0.0; }
-  for (int b = 0; b < B; ++b) {
+  float w[RHSEG_KERNEL_MAX_K], fwg[RHSEG_MAX_K], fwb[RHSEG_MAX_K];
+#pragma unroll
+  for (int k = 0; k < RHSEG_KERNEL_MAX_K; ++k) w[k] = (ok && k < K) ? head_w[(size_t)k * C + c] : 0.f;
+#pragma unroll
+  for (int j = 0; j < RHSEG_MAX_K; ++j) {
+    fwg[j] = (ok && film_w && j < K_prev) ? film_w[(size_t)c * K_prev + j] : 0.f;
+    fwb[j] = (ok && film_w && j < K_prev) ? film_w[(size_t)(C + c) * K_prev + j] : 0.f;
+  }
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  for (int b = bl; b < ((B + PG_BL - 1) / PG_BL) * PG_BL; b += PG_BL) {  // uniform trip count for the block reductions
+    const bool live = ok && b < B;
     double dgam = 0.0, dbet = 0.0;
-    if (ok) {
+    if (live) {
       const double gam = film_w ? (double)gamma_beta[(size_t)b * 2 * C + c] : 1.0;
       const double bet = film_w ? (double)gamma_beta[(size_t)b * 2 * C + C + c] : 0.0;
-      for (int k = 0; k < K; ++k) {
-        const double Sv = S[((size_t)b * K + k) * C + c], sv = s[b * K + k];
-        const double w = (double)head_w[(size_t)k * C + c];
-        dw[k] += Sv * gam + sv * bet;
-        dgam += Sv * w;
-        dbet += w * sv;
-      }
+#pragma unroll
+      for (int k = 0; k < RHSEG_KERNEL_MAX_K; ++k)
+        if (k < K) {
+          const double Sv = S[((size_t)b * K + k) * C + c], sv = s[b * K + k];
+          acc[k] += (float)(Sv * gam + sv * bet);
+          dgam += Sv * (double)w[k];
+          dbet += (double)w[k] * sv;
+        }
     }
     if (film_w) {
-      dfb_g += dgam;
-      dfb_b += dbet;
+      acc[RHSEG_KERNEL_MAX_K] += (float)dgam;
+      acc[RHSEG_KERNEL_MAX_K + 1] += (float)dbet;
       for (int j = 0; j < K_prev; ++j) {
-        const double cond = (double)(float)(prev_psum[b * K_prev + j] / n_pix);
-        dfw_g[j] += dgam * cond;
-        dfw_b[j] += dbet * cond;
-        double contrib = 0.0;
-        if (ok) contrib = (double)film_w[(size_t)c * K_prev + j] * dgam + (double)film_w[(size_t)(C + c) * K_prev + j] * dbet;
-        contrib = warp_sum(contrib);
-        if (lane == 0) atomicAdd(&g_prev[b * K_prev + j], contrib);
+        const double cond = b < B ? (double)(float)(prev_psum[b * K_prev + j] / n_pix) : 0.0;
+        acc[RHSEG_KERNEL_MAX_K + 2 + j] += (float)(dgam * cond);
+        acc[RHSEG_KERNEL_MAX_K + 2 + RHSEG_MAX_K + j] += (float)(dbet * cond);
+        // g_prev[b][j] = sum over channels of film_w^T [dgamma|dbeta]: the two warps that share (bl) reduce
+        const float contrib = warp_sum((float)((double)fwg[j] * dgam + (double)fwb[j] * dbet));
+        if (lane == 0) gsm[warp] = contrib;
+        __syncthreads();
+        if (cl == 0 && b < B) {
+          double tsum = 0.0;
+          for (int q = 0; q < PG_CH / 32; ++q) tsum += (double)gsm[bl * (PG_CH / 32) + q];
+          atomicAdd(&g_prev[b * K_prev + j], tsum);
+        }
+        __syncthreads();
       }
     }
   }
-  if (!ok) return;
-  for (int k = 0; k < K; ++k) d_head_w[(size_t)k * C + c] = (float)dw[k];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) red[bl][cl][i] = acc[i];
+  __syncthreads();
+  if (bl != 0 || !ok) return;
+  float tot[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    tot[i] = 0.f;
+#pragma unroll
+    for (int q = 0; q < PG_BL; ++q) tot[i] += red[q][cl][i];
+  }
+#pragma unroll
+  for (int k = 0; k < RHSEG_KERNEL_MAX_K; ++k)
+    if (k < K) d_head_w[(size_t)k * C + c] = tot[k];
   if (film_w) {
-    d_film_b[c] = (float)dfb_g;
-    d_film_b[C + c] = (float)dfb_b;
-    for (int j = 0; j < K_prev; ++j) {
-      d_film_w[(size_t)c * K_prev + j] = (float)dfw_g[j];
-      d_film_w[(size_t)(C + c) * K_prev + j] = (float)dfw_b[j];
-    }
+    d_film_b[c] = tot[RHSEG_KERNEL_MAX_K];
+    d_film_b[C + c] = tot[RHSEG_KERNEL_MAX_K + 1];
+#pragma unroll
+    for (int j = 0; j < RHSEG_MAX_K; ++j)
+      if (j < K_prev) {
+        d_film_w[(size_t)c * K_prev + j] = tot[RHSEG_KERNEL_MAX_K + 2 + j];
+        d_film_w[(size_t)(C + c) * K_prev + j] = tot[RHSEG_KERNEL_MAX_K + 2 + RHSEG_MAX_K + j];
+      }
   }
 }
 
@@ -520,7 +558,7 @@ extern "C" int rhseg_head_param_grads(const double* S, const double* s, const fl
     if (K_prev < 1 || K_prev > RHSEG_MAX_K) return RHSEG_ERR_UNSUPPORTED;
     RHSEG_CUDA(cudaMemsetAsync(g_prev, 0, sizeof(double) * (size_t)B * K_prev, st));
   }
-  param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(S, s, head_w, film_w, gamma_beta, prev_psum, n_pix, B, C, K, K_prev,
+  param_grads_kernel<<<(C + PG_CH - 1) / PG_CH, PG_THREADS, 0, st>>>(S, s, head_w, film_w, gamma_beta, prev_psum, n_pix, B, C, K, K_prev,
                                                       d_head_w, d_head_b, d_film_w, d_film_b, g_prev);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;

@@ -411,14 +411,20 @@ upsample_act_kernel(const float* __restrict__ z_lo, const float* __restrict__ pr
 #pragma unroll
     for (int v = 0; v < VEC; ++v) lx[v] = make_lerp(x0 + v, sx, Wf);
     const float* zb = z_lo + (size_t)b * K * Nf;
+    // neighbour offsets are shared by all K channels
+    int o00[VEC], o01[VEC], o10[VEC], o11[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      o00[v] = ly.i0 * Wf + lx[v].i0; o01[v] = ly.i0 * Wf + lx[v].i1;
+      o10[v] = ly.i1 * Wf + lx[v].i0; o11[v] = ly.i1 * Wf + lx[v].i1;
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const float* r0 = zb + (size_t)k * Nf + (size_t)ly.i0 * Wf;
-      const float* r1 = zb + (size_t)k * Nf + (size_t)ly.i1 * Wf;
+      const float* zk = zb + (size_t)k * Nf;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        const float a = __ldg(r0 + lx[v].i0), bq = __ldg(r0 + lx[v].i1);
-        const float c = __ldg(r1 + lx[v].i0), d = __ldg(r1 + lx[v].i1);
+        const float a = __ldg(zk + o00[v]), bq = __ldg(zk + o01[v]);
+        const float c = __ldg(zk + o10[v]), d = __ldg(zk + o11[v]);
         z[k][v] = ly.l0 * (lx[v].l0 * a + lx[v].l1 * bq) + ly.l1 * (lx[v].l0 * c + lx[v].l1 * d);
       }
     }
@@ -548,7 +554,7 @@ extern "C" int rhseg_film_fold(const float* head_w, const float* head_b, const f
     if (!film_b || !prev_psum || !gamma_beta || n_pix <= 0) return RHSEG_ERR_ARG;
     if (K_prev < 1 || K_prev > RHSEG_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   }
-  const int threads = 256;
+  const int threads = C >= 512 ? 768 : 256;
   const size_t smem = (RHSEG_MAX_K + RHSEG_KERNEL_MAX_K * (threads / 32)) * sizeof(float);
   film_fold_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(head_w, head_b, film_w, film_b, prev_psum, n_pix, C, K,
                                                              K_prev, gamma_beta, eff_w, eff_b);

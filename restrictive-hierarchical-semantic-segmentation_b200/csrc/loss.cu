@@ -49,8 +49,8 @@ loss_stats_kernel(const float* __restrict__ outs, const float* __restrict__ targ
         float zz[K], mx, sum;
 #pragma unroll
         for (int k = 0; k < K; ++k) zz[k] = z[k][v];
-        full_softmax<K>(zz, p, mx, sum);
-        const float lse = logf(sum);
+        fast_softmax<K>(zz, p, mx, sum);
+        const float lse = __logf(sum);
 #pragma unroll
         for (int k = 0; k < K; ++k) lp[k] = (zz[k] - mx) - lse;
       } else {
@@ -168,31 +168,116 @@ struct StepLevels {
   int child[RHSEG_MAX_LEVELS];
 };
 
+// Per-sample CE / Dice terms of one (level, sample): shared by both finalize kernels' fast path.
+struct SampleLoss {
+  double ce, dice;
+  bool ce_nan, dice_ok;
+};
+__device__ __forceinline__ SampleLoss sample_loss(const double* __restrict__ st, const float* __restrict__ weights,
+                                                  int K, int B, double smooth, float* __restrict__ cf) {
+  constexpr int NS = RHSEG_NSTAT;
+  SampleLoss r;
+  double ce = 0.0, I = 0.0, U = 0.0;
+  bool ce_nan = false;
+  for (int c = 0; c < K; ++c) {
+    const double w = (double)weights[c];
+    const double cnt = st[c * NS + 1];
+    if (cnt == 0.0) ce_nan = true;
+    else ce += -(w * st[c * NS + 0]) / cnt;
+    I += w * st[c * NS + 2];
+    U += w * st[c * NS + 3] + w * st[c * NS + 4];
+  }
+  ce = ce / (double)K;
+  if (ce != ce) ce_nan = true;
+  const double num = 2.0 * I + smooth, den = U + smooth;
+  const double dl = 1.0 - num / den;
+  r.ce_nan = ce_nan;
+  r.ce = ce_nan ? 1.0 : ce;
+  r.dice_ok = !(dl != dl);
+  r.dice = r.dice_ok ? dl : 0.0;
+  for (int c = 0; c < K; ++c) {
+    const double w = (double)weights[c];
+    const double cnt = st[c * NS + 1];
+    cf[c * 3 + 0] = ce_nan ? 0.f : (float)(-w / (cnt * (double)K * (double)B));
+    cf[c * 3 + 1] = r.dice_ok ? (float)(w * (-2.0 / den)) : 0.f;   // scaled by 1/n_valid afterwards
+    cf[c * 3 + 2] = r.dice_ok ? (float)(w * (num / (den * den))) : 0.f;
+  }
+  return r;
+}
+
+// All levels in parallel: thread <-> (level, sample); shared-memory fp64 atomics per level.
 __global__ void __launch_bounds__(256)
 step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ weights, StepLevels lv, int B,
                      double smooth, double inv_bn, float* __restrict__ out, float* __restrict__ coef) {
-  __shared__ double sh[4][256];
-  size_t w_off = 0, k_off = 0, c_off = 0;
-  double cons_total = 0.0;
-  int cons_count = 0;
-  for (int L = 0; L < lv.n_levels; ++L) {
-    const int K = lv.K[L];
-    const int nc = lv.child[L] ? K + 1 : K;
-    const double* stats = ws + w_off;
-    finalize_level(stats, weights + k_off, B, K, smooth, out + 2 + 4 * L, coef + c_off, sh);
-    const double* cons = stats + (size_t)B * K * RHSEG_NSTAT;
-    for (int g = 0; g < lv.G[L]; ++g) cons_total += cons[g] * inv_bn;  // mean |children - parent| of group g
-    cons_count += lv.G[L];
-    w_off += (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K + (size_t)nc * nc;
-    k_off += K;
-    c_off += (size_t)B * K * 3;
+  __shared__ double acc[RHSEG_MAX_LEVELS][4];  // ce_sum, dice_sum, n_dice, n_ce
+  __shared__ size_t w_off[RHSEG_MAX_LEVELS + 1], k_off[RHSEG_MAX_LEVELS + 1], c_off[RHSEG_MAX_LEVELS + 1], r_off[RHSEG_MAX_LEVELS + 1];
+  const int tid = threadIdx.x, nL = lv.n_levels;
+  if (tid == 0) {
+    w_off[0] = k_off[0] = c_off[0] = 0;
+    r_off[0] = 2 + 4 * (size_t)nL;
+    for (int L = 0; L < nL; ++L) {
+      const int K = lv.K[L], nc = lv.child[L] ? K + 1 : K;
+      w_off[L + 1] = w_off[L] + (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K + (size_t)nc * nc;
+      k_off[L + 1] = k_off[L] + K;
+      c_off[L + 1] = c_off[L] + (size_t)B * K * 3;
+      r_off[L + 1] = r_off[L] + 5 * (size_t)nc;
+    }
   }
-  if (threadIdx.x == 0) {
-    const float cons = cons_count > 0 ? (float)(cons_total / (double)cons_count) : 0.f;
-    float total = cons;
-    for (int L = 0; L < lv.n_levels; ++L) total += out[2 + 4 * L] + out[2 + 4 * L + 1];  // CE_L + Dice_L (0 when none valid)
-    out[0] = total;
-    out[1] = cons;
+  if (tid < RHSEG_MAX_LEVELS * 4) (&acc[0][0])[tid] = 0.0;
+  __syncthreads();
+  for (int e = tid; e < nL * B; e += blockDim.x) {
+    const int L = e / B, b = e - L * B, K = lv.K[L];
+    const SampleLoss r = sample_loss(ws + w_off[L] + (size_t)b * K * RHSEG_NSTAT, weights + k_off[L], K, B, smooth,
+                                     coef + c_off[L] + (size_t)b * K * 3);
+    atomicAdd(&acc[L][0], r.ce);
+    if (r.dice_ok) { atomicAdd(&acc[L][1], r.dice); atomicAdd(&acc[L][2], 1.0); }
+    if (!r.ce_nan) atomicAdd(&acc[L][3], 1.0);
+  }
+  __syncthreads();
+  // dice coefficients carry 1/n_valid of their level
+  for (int L = 0; L < nL; ++L) {
+    const float inv_nv = acc[L][2] > 0.0 ? (float)(1.0 / acc[L][2]) : 0.f;
+    float* cf = coef + c_off[L];
+    for (int i = tid; i < B * lv.K[L]; i += blockDim.x) {
+      cf[(size_t)i * 3 + 1] *= inv_nv;
+      cf[(size_t)i * 3 + 2] *= inv_nv;
+    }
+  }
+  // the five per-class ratios of every level (same arithmetic as rhseg_metric_ratios)
+  for (int L = 0; L < nL; ++L) {
+    const int K = lv.K[L], nc = lv.child[L] ? K + 1 : K;
+    if (tid < nc) {
+      const long long* conf = reinterpret_cast<const long long*>(ws + w_off[L] + (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K);
+      const int c = tid;
+      long long tp = conf[c * nc + c], row = 0, col = 0;
+      for (int j = 0; j < nc; ++j) { row += conf[c * nc + j]; col += conf[j * nc + c]; }
+      const long long fp = col - tp, fn = row - tp;
+      auto safe = [](float num, float den) { return num / (den == 0.f ? 1.f : den); };
+      const float tpf = (float)tp, fpf = (float)fp, fnf = (float)fn;
+      float* o = out + r_off[L];
+      o[0 * nc + c] = safe(2.0f * tpf, (2.0f * tpf + 1.0f * fnf) + fpf);
+      o[1 * nc + c] = safe(tpf, (float)(col + row - tp));
+      o[2 * nc + c] = safe(tpf, (float)(tp + fn));
+      o[3 * nc + c] = safe(tpf, (float)(tp + fp));
+      o[4 * nc + c] = safe(tpf, (float)(tp + fn));
+    }
+  }
+  if (tid == 0) {
+    double cons_total = 0.0;
+    int cons_count = 0;
+    float total = 0.f;
+    for (int L = 0; L < nL; ++L) {
+      const double* cons = ws + w_off[L] + (size_t)B * lv.K[L] * RHSEG_NSTAT;
+      for (int g = 0; g < lv.G[L]; ++g) cons_total += cons[g] * inv_bn;  // mean |children - parent| of group g
+      cons_count += lv.G[L];
+      const float ce = (float)(acc[L][0] / (double)B);
+      const float dice = acc[L][2] > 0.0 ? (float)(acc[L][1] / acc[L][2]) : 0.f;
+      out[2 + 4 * L] = ce; out[3 + 4 * L] = dice; out[4 + 4 * L] = (float)acc[L][2]; out[5 + 4 * L] = (float)acc[L][3];
+      total += ce + dice;  // CE_L + Dice_L (0 when no sample is valid)
+    }
+    const float consf = cons_count > 0 ? (float)(cons_total / (double)cons_count) : 0.f;
+    out[0] = total + consf;
+    out[1] = consf;
   }
 }
 

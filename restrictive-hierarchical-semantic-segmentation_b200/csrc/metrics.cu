@@ -5,9 +5,6 @@
 
 namespace rhseg {
 
-// torch.argmax semantics: first maximum, NaN counts as the maximum.
-__device__ __forceinline__ bool beats(float v, float best) { return (v > best) || (v != v && best == best); }
-
 // class index of one pixel following ProcessClasses (performance_metrics.py:31-47)
 template <int K>
 __device__ __forceinline__ int process_class(const float (&x)[K], bool child) {
@@ -33,15 +30,53 @@ __device__ __forceinline__ int process_class(const float (&x)[K], bool child) {
 // argmax(softmax(z)) with ATen's op order (train.py:219-221)
 template <int K>
 __device__ __forceinline__ int argmax_softmax(const float (&z)[K]) {
-  float p[K], mx, sum;
-  full_softmax<K>(z, p, mx, sum);
-  float best = p[0];
-  int idx = 0;
-#pragma unroll
-  for (int k = 1; k < K; ++k)
-    if (beats(p[k], best)) { best = p[k]; idx = k; }
-  return idx;
+  return argmax_softmax_aten<K>(z);
 }
+
+// Warp-cooperative confusion counting without atomics or match: every lane owns up to SLOTS
+// cells (cell = lane + 32*slot) and counts, from 2*nc ballots, how many lanes of the warp hold
+// (target class a, predicted class b).  tc < 0 marks an ignored pixel.
+template <int NCMAX>
+struct WarpConfusion {
+  static constexpr int SLOTS = (NCMAX * NCMAX + 31) / 32;
+  int cnt[SLOTS];
+  int my_a[SLOTS], my_b[SLOTS];
+  __device__ __forceinline__ void init(int nc) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const int cell = lane + 32 * s;
+      cnt[s] = 0;
+      my_a[s] = cell < nc * nc ? cell / nc : -2;
+      my_b[s] = cell < nc * nc ? cell % nc : -2;
+    }
+  }
+  __device__ __forceinline__ void add(int tc, int pc) {
+    unsigned ma[SLOTS], mb[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) { ma[s] = 0u; mb[s] = 0u; }
+#pragma unroll
+    for (int c = 0; c < NCMAX; ++c) {
+      const unsigned ta = __ballot_sync(0xffffffffu, tc == c);
+      const unsigned pb = __ballot_sync(0xffffffffu, pc == c);
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) {
+        if (my_a[s] == c) ma[s] = ta;
+        if (my_b[s] == c) mb[s] = pb;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) cnt[s] += __popc(ma[s] & mb[s]);
+  }
+  __device__ __forceinline__ void flush(int* hist, int nc) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const int cell = lane + 32 * s;
+      if (cell < nc * nc && cnt[s]) atomicAdd(&hist[cell], cnt[s]);
+    }
+  }
+};
 
 // warp-aggregated histogram update: lanes holding the same cell elect one leader
 __device__ __forceinline__ void hist_add(int* hist, int cell) {
@@ -63,6 +98,8 @@ confusion_kernel(const float* __restrict__ probs, long p_bstride, long p_cstride
   __syncthreads();
   const float* pb = probs + (size_t)b * p_bstride;
   const float* tb = targets + (size_t)b * t_bstride;
+  WarpConfusion<K + 1> wc;
+  wc.init(nc);
   const long chunk0 = (long)blockIdx.x * (THREADS * VEC * ITER);
 #pragma unroll
   for (int it = 0; it < ITER; ++it) {
@@ -95,15 +132,13 @@ confusion_kernel(const float* __restrict__ probs, long p_bstride, long p_cstride
           tg[k] = ign ? 0.0f : tg[k];                // eval target
         }
       }
-      int cell = -1;
-      if (ok) {
-        const int pc = process_class<K>(pr, child != 0);
-        const int tc = process_class<K>(tg, child != 0);
-        if (!(child && tc == 0)) cell = tc * nc + pc;  // torchmetrics ignore_index=0 on child levels
-      }
-      hist_add(hist, cell);
+      const int pc = process_class<K>(pr, child != 0);
+      int tc = process_class<K>(tg, child != 0);
+      if (!ok || (child && tc == 0)) tc = -1;  // torchmetrics ignore_index=0 on child levels
+      wc.add(tc, pc);
     }
   }
+  wc.flush(hist, nc);
   __syncthreads();
   for (int i = tid; i < nc * nc; i += THREADS)
     if (hist[i]) atomicAdd(&conf[i], (unsigned long long)hist[i]);
@@ -195,6 +230,8 @@ level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ ta
   __syncthreads();
   const bool do_cons = child && prev_idx != nullptr && parent_targets != nullptr;
   const LevelInfo li = load_level_info<K>(child ? table : nullptr);
+  WarpConfusion<K + 1> wc;
+  wc.init(nc);
   float a[K][NS], ca[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -244,14 +281,9 @@ level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ ta
       float zz[K], p[K], mx, sum;
 #pragma unroll
       for (int k = 0; k < K; ++k) zz[k] = z[k][v];
-      full_softmax<K>(zz, p, mx, sum);
-      const float lse = logf(sum);
-      // prediction: first maximum of the softmax (torch.argmax semantics)
-      float best = p[0];
-      int idx = 0;
-#pragma unroll
-      for (int k = 1; k < K; ++k)
-        if (beats(p[k], best)) { best = p[k]; idx = k; }
+      fast_softmax<K>(zz, p, mx, sum);
+      const float lse = __logf(sum);
+      const int idx = argmax_softmax_aten<K>(zz);  // train.py:219-221, bit-exact
       my_idx[v] = (unsigned char)idx;
       float pr[K], et[K];
 #pragma unroll
@@ -269,13 +301,17 @@ level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ ta
         pr[k] = (k == idx && m) ? 1.0f : 0.0f;
         et[k] = m ? tk : 0.0f;
       }
-      int cell = -1;
-      if (ok) {
-        const int pc = process_class<K>(pr, child != 0);
-        const int tc = process_class<K>(et, child != 0);
-        if (!(child && tc == 0)) cell = tc * nc + pc;
+      {
+        // ProcessClasses of the masked one-hot prediction: the predicted channel if its target is
+        // not ignored, otherwise "nothing positive" (class 0 on child levels, argmax of zeros = 0 else)
+        float pm = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) pm += pr[k];
+        const int pc = pm != 0.f ? (child ? idx + 1 : idx) : 0;
+        int tc = process_class<K>(et, child != 0);
+        if (!ok || (child && tc == 0)) tc = -1;  // out of range / torchmetrics ignore_index=0 on child levels
+        wc.add(tc, pc);
       }
-      hist_add(hist, cell);
       if (do_cons && ok) {
         float gs[K];
         group_sum<K>(pr, li.start_mask, gs);  // children one-hots summed per group
@@ -314,6 +350,8 @@ level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ ta
     if (tid < K * NS) atomicAdd(&stats[(size_t)b * K * NS + tid], acc);
     else if (do_cons && ((li.start_mask >> (tid - K * NS)) & 1)) atomicAdd(&cons[table[RHSEG_TBL_GROUP_OF + tid - K * NS]], acc);
   }
+  wc.flush(hist, nc);
+  __syncthreads();
   for (int i = tid; i < nc * nc; i += THREADS)
     if (hist[i]) atomicAdd(&conf[i], (unsigned long long)hist[i]);
 }

@@ -14,6 +14,7 @@
 namespace rhseg {
 
 constexpr int ADJ_TH = 8, ADJ_TW = 16, ADJ_THREADS = 256;
+constexpr int ADJ_MAXW = 24;  // max hi-res taps per low-res index held in the weight tables (upsampling factor <= ~10)
 
 struct FusedDzArgs {
   const float* logits;      // [B,K,H,W]
@@ -50,14 +51,45 @@ upsample_adjoint_tiled_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, i
   const int ry = y1 - y0 + 1, rx = x1 - x0 + 1;  // <= ry_max, rx_max by construction of the launcher
   const long N = (long)H * W;
 
+  // interpolation weight tables of this tile: for output column j0+tj the contiguous run of hi-res
+  // columns [wx_start, wx_start+wx_cnt) that read it, with their weights (same for rows)
+  __shared__ float wx_tab[ADJ_TW * ADJ_MAXW], wy_tab[ADJ_TH * ADJ_MAXW];
+  __shared__ int wx_start[ADJ_TW], wx_cnt[ADJ_TW], wy_start[ADJ_TH], wy_cnt[ADJ_TH];
+  if (tid < ADJ_TW + ADJ_TH) {
+    const bool is_x = tid < ADJ_TW;
+    const int t = is_x ? tid : tid - ADJ_TW;
+    const int lim = is_x ? tw : th;
+    if (t < lim) {
+      const int want = (is_x ? j0 : i0) + t;
+      const float sc = is_x ? sx : sy;
+      const int in_size = is_x ? Wf : Hf, out_size = is_x ? W : H;
+      int lo, hi;
+      lerp_support(want, sc, out_size, lo, hi);
+      int first = -1, cnt = 0;
+      float* tab = (is_x ? wx_tab : wy_tab) + t * ADJ_MAXW;
+      for (int o = lo; o <= hi; ++o) {
+        const float w = lerp_weight(o, sc, in_size, want);
+        if (w != 0.f || first >= 0) {
+          if (first < 0) first = o;
+          if (cnt < ADJ_MAXW) tab[cnt] = w;
+          ++cnt;
+        }
+      }
+      // trailing zeros are harmless; the run is contiguous because the weights form a hat function
+      (is_x ? wx_start : wy_start)[t] = first < 0 ? lo : first;
+      (is_x ? wx_cnt : wy_cnt)[t] = cnt < ADJ_MAXW ? cnt : ADJ_MAXW;
+    }
+  }
+
   // ---- phase 1: hi-res gradient of the region -> shared memory ----
   if constexpr (SRC == 0) {
-    for (int e = tid; e < K * ry * rx; e += ADJ_THREADS) {
-      const int k = e / (ry * rx);
-      const int r = e - k * (ry * rx);
-      const int yy = r / rx, xx = r - yy * rx;
-      reg[((size_t)k * ry_max + yy) * rx_max + xx] = __ldg(dz_hi + ((size_t)b * K + k) * N + (size_t)(y0 + yy) * W + x0 + xx);
-    }
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int yy = warp; yy < ry; yy += ADJ_THREADS / 32)
+      for (int xx = lane; xx < rx; xx += 32) {
+        const float* src = dz_hi + (size_t)b * K * N + (size_t)(y0 + yy) * W + x0 + xx;
+#pragma unroll
+        for (int k = 0; k < K; ++k) reg[((size_t)k * ry_max + yy) * rx_max + xx] = __ldg(src + (size_t)k * N);
+      }
   } else {
     const LevelInfo li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? fa.table : nullptr);
     const float gce = fa.g_ce ? __ldg(fa.g_ce) : 0.f, gdi = fa.g_dice ? __ldg(fa.g_dice) : 0.f;
@@ -71,8 +103,9 @@ upsample_adjoint_tiled_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, i
       gu[k] = fa.g_uniform ? (float)fa.g_uniform[b * K + k] * fa.inv_npix : 0.f;
     }
     const bool has_act = MODE != RHSEG_ACT_ZEROS && (fa.g_uniform != nullptr || (fa.dp_pix != nullptr && fa.pix_mask != 0));
-    for (int r = tid; r < ry * rx; r += ADJ_THREADS) {
-      const int yy = r / rx, xx = r - yy * rx;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int yy = warp; yy < ry; yy += ADJ_THREADS / 32)
+     for (int xx = lane; xx < rx; xx += 32) {
       const int y = y0 + yy, x = x0 + xx;
       const size_t px = (size_t)y * W + x;
       float z[K], t[K], dz[K];
@@ -116,35 +149,37 @@ upsample_adjoint_tiled_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, i
   __syncthreads();
 
   // ---- phase 2: reduce along x: tmp[k][yy][tj] = sum_x wx(x, j0+tj) reg[k][yy][x] ----
-  for (int e = tid; e < K * ry * tw; e += ADJ_THREADS) {
-    const int tj = e % tw;
-    const int r = e / tw;
-    const int yy = r % ry, k = r / ry;
-    int xa, xb;
-    lerp_support(j0 + tj, sx, W, xa, xb);
-    const float* row = reg + ((size_t)k * ry_max + yy) * rx_max;
-    float acc = 0.f;
-    for (int x = xa; x <= xb; ++x) {
-      const float w = lerp_weight(x, sx, Wf, j0 + tj);
-      if (w != 0.f) acc = fmaf(w, row[x - x0], acc);
+  // (the few non-zero interpolation weights per output column / row were tabulated once per CTA)
+  {
+    const int tj = tid & (ADJ_TW - 1), rslot = tid / ADJ_TW;
+    if (tj < tw) {
+      const int xs = wx_start[tj] - x0, xn = wx_cnt[tj];
+      const float* wt = wx_tab + tj * ADJ_MAXW;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        for (int yy = rslot; yy < ry; yy += ADJ_THREADS / ADJ_TW) {
+          const float* row = reg + ((size_t)k * ry_max + yy) * rx_max + xs;
+          float acc = 0.f;
+          for (int q = 0; q < xn; ++q) acc = fmaf(wt[q], row[q], acc);
+          tmp[((size_t)k * ry_max + yy) * ADJ_TW + tj] = acc;
+        }
     }
-    tmp[((size_t)k * ry_max + yy) * ADJ_TW + tj] = acc;
   }
   __syncthreads();
 
   // ---- phase 3: reduce along y and store ----
-  for (int e = tid; e < K * th * tw; e += ADJ_THREADS) {
-    const int tj = e % tw;
-    const int r = e / tw;
-    const int ti = r % th, k = r / th;
-    int ya, yb;
-    lerp_support(i0 + ti, sy, H, ya, yb);
-    float acc = 0.f;
-    for (int y = ya; y <= yb; ++y) {
-      const float w = lerp_weight(y, sy, Hf, i0 + ti);
-      if (w != 0.f) acc = fmaf(w, tmp[((size_t)k * ry_max + (y - y0)) * ADJ_TW + tj], acc);
+  {
+    const int tj = tid & (ADJ_TW - 1), ti = (tid / ADJ_TW) & (ADJ_TH - 1), kslot = tid / (ADJ_TW * ADJ_TH);
+    if (tj < tw && ti < th) {
+      const int ys = wy_start[ti] - y0, yn = wy_cnt[ti];
+      const float* wt = wy_tab + ti * ADJ_MAXW;
+      for (int k = kslot; k < K; k += ADJ_THREADS / (ADJ_TW * ADJ_TH)) {
+        const float* col = tmp + ((size_t)k * ry_max + ys) * ADJ_TW + tj;
+        float acc = 0.f;
+        for (int q = 0; q < yn; ++q) acc = fmaf(wt[q], col[q * ADJ_TW], acc);
+        dz_lo[((size_t)b * K + k) * Hf * Wf + (size_t)(i0 + ti) * Wf + j0 + tj] = acc;
+      }
     }
-    dz_lo[((size_t)b * K + k) * Hf * Wf + (size_t)(i0 + ti) * Wf + j0 + tj] = acc;
   }
 }
 
@@ -241,6 +276,9 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
   const int ry_max = region_extent(ADJ_TH, sy, H), rx_max = region_extent(ADJ_TW, sx, W) | 1;  // odd pitch: fewer bank conflicts
   const size_t smem = ((size_t)K * ry_max * rx_max + (size_t)K * ry_max * ADJ_TW) * sizeof(float);
   if (smem > 200 * 1024) return RHSEG_ERR_UNSUPPORTED;  // upsampling factor too large for the tiled kernel
+  if (sy > 0.f && 2.0f / sy + 4.0f > (float)ADJ_MAXW) return RHSEG_ERR_UNSUPPORTED;
+  if (sx > 0.f && 2.0f / sx + 4.0f > (float)ADJ_MAXW) return RHSEG_ERR_UNSUPPORTED;
+  if ((sy <= 0.f && H > ADJ_MAXW) || (sx <= 0.f && W > ADJ_MAXW)) return RHSEG_ERR_UNSUPPORTED;
   auto kern = upsample_adjoint_tiled_kernel<K, SRC, MODE>;
   if (smem > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((Wf + ADJ_TW - 1) / ADJ_TW, (Hf + ADJ_TH - 1) / ADJ_TH, B);

@@ -87,19 +87,20 @@ class _FusedStepFn(torch.autograd.Function):
             call("rhseg_level_eval", ptr(r["logits"][L]), t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs,
                  ptr(idx_maps[L - 1]) if L > 0 else None, ptr(tables[L]), B, K, n_pix, 1 if L > 0 else 0,
                  ws.data_ptr() + offs[L][0] * 8, ptr(idx_maps[L]), st)
-        scalars = torch.empty((2 + 4 * n,), dtype=torch.float32, device=dev)
+        n_ratio = sum(5 * o[3] for o in offs)
+        scal_all = torch.empty((2 + 4 * n + n_ratio,), dtype=torch.float32, device=dev)
+        scalars = scal_all[:2 + 4 * n]
         coef_all = torch.empty((B * sum(tree.head_channels) * 3,), dtype=torch.float32, device=dev)
         Ks = (_I32 * n)(*tree.head_channels)
         Gs = (_I32 * n)(*[tree.group_count(L) for L in range(n)])
-        call("rhseg_step_finalize", ptr(ws), ptr(weights_all), B, n, Ks, Gs, float(smooth), n_pix, ptr(scalars),
+        call("rhseg_step_finalize", ptr(ws), ptr(weights_all), B, n, Ks, Gs, float(smooth), n_pix, ptr(scal_all),
              ptr(coef_all), st)
-        conf, ratios = [], []
+        conf, ratios, r_off = [], [], 2 + 4 * n
         for L in range(n):
             nc = offs[L][3]
-            c = ws[offs[L][2]:offs[L][2] + nc * nc].view(torch.int64).view(nc, nc)
-            rt = torch.empty((5, nc), dtype=torch.float32, device=dev)
-            call("rhseg_metric_ratios", ptr(c), nc, ptr(rt), st)
-            conf.append(c); ratios.append(rt)
+            conf.append(ws[offs[L][2]:offs[L][2] + nc * nc].view(torch.int64).view(nc, nc))
+            ratios.append(scal_all[r_off:r_off + 5 * nc].view(5, nc))
+            r_off += 5 * nc
         ctx.tree, ctx.dims, ctx.upsampled = tree, r["dims"], r["upsampled"]
         ctx.t_meta = (t_bs, t_cs, ch_off, esz)
         ctx.save_for_backward(target, coef_all, *r["feats"], *r["head_w"], *r["film_w"], *r["logits"], *r["probs"],
