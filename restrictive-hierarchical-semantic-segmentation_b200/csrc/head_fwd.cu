@@ -464,6 +464,93 @@ upsample_act_kernel(const float* __restrict__ z_lo, const float* __restrict__ pr
   block_psum<K, THREADS / 32>(ps, psum + (size_t)b * K, red, [] { __syncthreads(); });
 }
 
+// Tiled variant for upsampling factors >= 1 (the HRNet case): a CTA of 16x16 threads owns a
+// 16 x (16*VEC) hi-res tile, stages the low-res logit patch it reads in shared memory and
+// interpolates from there (shared-memory loads with immediate offsets instead of 64 global loads
+// with 64-bit address arithmetic per thread).
+template <int K, int VEC, int MODE>
+__global__ void __launch_bounds__(256)
+upsample_act_tiled_kernel(const float* __restrict__ z_lo, const float* __restrict__ prev_probs,
+                          const int32_t* __restrict__ table, int Hf, int Wf, int H, int W, int K_prev, float sy,
+                          float sx, float* __restrict__ logits, float* __restrict__ probs, double* __restrict__ psum) {
+  constexpr int TH = 16, TW = 16 * VEC;
+  constexpr int PH = TH + 2, PW = TW + 2;  // patch bound for scale <= 1
+  __shared__ float patch[K][PH][PW];
+  __shared__ float red[8 * K];
+  const int b = blockIdx.z, tid = threadIdx.x;
+  const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+  const int ylast = min(ty0 + TH, H) - 1, xlast = min(tx0 + TW, W) - 1;
+  const int r0 = (int)(sy * (float)ty0), c0 = (int)(sx * (float)tx0);
+  const int r1 = min((int)(sy * (float)ylast) + 1, Hf - 1), c1 = min((int)(sx * (float)xlast) + 1, Wf - 1);
+  const int ph = r1 - r0 + 1, pw = c1 - c0 + 1;
+  const long N = (long)H * W, Nf = (long)Hf * Wf;
+  {
+    const float* zb = z_lo + (size_t)b * K * Nf;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int kr = warp; kr < K * ph; kr += 8) {
+      const int k = kr / ph, rr = kr - k * ph;
+      const float* src = zb + (size_t)k * Nf + (size_t)(r0 + rr) * Wf + c0;
+      for (int cc = lane; cc < pw; cc += 32) patch[k][rr][cc] = __ldg(src + cc);
+    }
+  }
+  __syncthreads();
+  const int y = ty0 + (tid >> 4), x0 = tx0 + (tid & 15) * VEC;
+  const bool ok = y < H && x0 < W;  // W % VEC == 0 guaranteed by the launcher
+  const LevelInfo li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? table : nullptr);
+  const long px = (long)y * W + x0;
+  float z[K][VEC], pp[K][VEC], prob[K][VEC];
+  if (ok) {
+    const Lerp ly = make_lerp(y, sy, Hf);
+    const int row0 = (ly.i0 - r0) * PW, row1 = (ly.i1 - r0) * PW;
+    const float* pbase = &patch[0][0][0];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const Lerp lx = make_lerp(x0 + v, sx, Wf);
+      const float* p00 = pbase + row0 + (lx.i0 - c0);
+      const float* p01 = pbase + row0 + (lx.i1 - c0);
+      const float* p10 = pbase + row1 + (lx.i0 - c0);
+      const float* p11 = pbase + row1 + (lx.i1 - c0);
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        z[k][v] = ly.l0 * (lx.l0 * p00[k * PH * PW] + lx.l1 * p01[k * PH * PW]) +
+                  ly.l1 * (lx.l0 * p10[k * PH * PW] + lx.l1 * p11[k * PH * PW]);
+    }
+    if constexpr (MODE == RHSEG_ACT_GROUPED) {
+      const float* pb = prev_probs + (size_t)b * K_prev * N;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if ((li.start_mask >> k) & 1) {
+          const Vec<VEC> t = ld_cached<VEC>(pb + (size_t)li.parent[k] * N + px);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) pp[k][v] = t.v[v];
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) pp[k][v] = pp[k > 0 ? k - 1 : 0][v];
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { z[k][v] = 0.f; pp[k][v] = 0.f; }
+  }
+  activate<K, VEC, MODE>(z, pp, li.start_mask, prob);
+  float ps[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    ps[k] = 0.f;
+    if (ok) {
+      Vec<VEC> zo, po;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { zo.v[v] = z[k][v]; po.v[v] = prob[k][v]; ps[k] += po.v[v]; }
+      *reinterpret_cast<Vec<VEC>*>(logits + ((size_t)b * K + k) * N + px) = zo;
+      *reinterpret_cast<Vec<VEC>*>(probs + ((size_t)b * K + k) * N + px) = po;
+    }
+  }
+  block_psum<K, 8>(ps, psum + (size_t)b * K, red, [] { __syncthreads(); });
+}
+
 template <int K, int VEC, int J, int MODE, typename CFG>
 static int launch_fwd(const float* feats, const float* eff_w, const float* eff_b, const float* prev_probs,
                       const int32_t* table, int B, int C, int N, int K_prev, float* logits, float* probs,
@@ -526,6 +613,17 @@ static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32
   const float sy = H > 1 ? (float)(Hf - 1) / (float)(H - 1) : 0.f;
   const float sx = W > 1 ? (float)(Wf - 1) / (float)(W - 1) : 0.f;
   constexpr int THREADS = 256;
+  if (sy <= 1.0f && sx <= 1.0f) {  // upsampling: tiled kernel
+    if (W % 4 == 0) {
+      dim3 grid((W + 63) / 64, (H + 15) / 16, B);
+      upsample_act_tiled_kernel<K, 4, MODE><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, logits, probs, psum);
+    } else {
+      dim3 grid((W + 15) / 16, (H + 15) / 16, B);
+      upsample_act_tiled_kernel<K, 1, MODE><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, logits, probs, psum);
+    }
+    RHSEG_LAUNCH_CHECK();
+    return RHSEG_OK;
+  }
   if (W % 4 == 0) {
     const int vps = H * (W / 4);
     dim3 grid((vps + THREADS - 1) / THREADS, B);

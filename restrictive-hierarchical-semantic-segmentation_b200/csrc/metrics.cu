@@ -1,6 +1,7 @@
 // Metrics: integer confusion matrix (ProcessClasses + torchmetrics multiclass semantics,
 // Metrics/performance_metrics.py:27-141) and the train-loop prediction glue
 // (train.py:206-231, predictEval.py:409-422).
+#include <algorithm>
 #include "common.cuh"
 
 namespace rhseg {
@@ -213,7 +214,7 @@ __global__ void metric_ratios_kernel(const long long* __restrict__ conf, int nc,
 // out layout (8-byte words): [B*K*5 fp64 stats][RHSEG_MAX_K fp64 consistency sums][nc*nc int64 confusion]
 // ------------------------------------------------------------------------------------
 template <int K, int VEC, int ITER, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ targets, long t_bstride, long t_cstride,
                   const float* __restrict__ parent_targets, long pt_bstride, long pt_cstride,
                   const unsigned char* __restrict__ prev_idx, const int32_t* __restrict__ table, long N, int child,
@@ -241,10 +242,9 @@ level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ ta
   }
   const float* zb = logits + (size_t)b * K * N;
   const float* tb = targets + (size_t)b * t_bstride;
-  const long chunk0 = (long)blockIdx.x * (THREADS * VEC * ITER);
-#pragma unroll
-  for (int it = 0; it < ITER; ++it) {
-    const long px = chunk0 + (long)it * THREADS * VEC + (long)tid * VEC;
+  // persistent over the sample's pixel vectors: one resident wave, statistics reduced once per CTA
+  for (long px0 = (long)blockIdx.x * (THREADS * VEC); px0 < N; px0 += (long)gridDim.x * (THREADS * VEC)) {
+    const long px = px0 + (long)tid * VEC;
     const bool ok = px < N;
     float z[K][VEC], t[K][VEC], ptv[K][VEC];
     unsigned char pidx[VEC];
@@ -447,17 +447,18 @@ extern "C" int rhseg_level_eval(const float* logits, const float* targets, long 
   double* cons = stats + (size_t)B * K * RHSEG_NSTAT;
   unsigned long long* conf = reinterpret_cast<unsigned long long*>(cons + RHSEG_MAX_K);
   const long N = n_pix;
-  constexpr int THREADS = 256, ITER = 2;
+  constexpr int THREADS = 256, ITER = 1;
+  const int slots = std::max(1, device_sm_count() * 2 / B);  // CTAs per sample for one resident wave (2 CTAs/SM)
   bool v4 = (N % 4 == 0) && aligned16(logits) && aligned16(targets) && t_bstride % 4 == 0 && t_cstride % 4 == 0 &&
             (reinterpret_cast<uintptr_t>(prev_idx) % 4 == 0) && (reinterpret_cast<uintptr_t>(idx_out) % 4 == 0);
   if (parent_targets) v4 = v4 && aligned16(parent_targets) && pt_bstride % 4 == 0 && pt_cstride % 4 == 0;
   RHSEG_DISPATCH_K(K, {
     if (v4) {
-      dim3 grid((unsigned)((N + THREADS * 4 * ITER - 1) / (THREADS * 4 * ITER)), B);
+      dim3 grid((unsigned)std::min<long>(slots, (N + THREADS * 4 - 1) / (THREADS * 4)), B);
       level_eval_kernel<KK, 4, ITER, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
           pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     } else {
-      dim3 grid((unsigned)((N + THREADS * ITER - 1) / (THREADS * ITER)), B);
+      dim3 grid((unsigned)std::min<long>(slots, (N + THREADS - 1) / THREADS), B);
       level_eval_kernel<KK, 1, ITER, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
           pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     }
