@@ -129,6 +129,7 @@ class GpuStep:
         leaves = self.feats + [p for grp in self.params for p in grp]
         self.grads = torch.autograd.grad(out.loss, leaves)  # dfeats per level + head / FiLM parameter grads
         self.result = (out.scalars, out.ratios)
+        self.confusion = out.confusion
         return self.result
 
     def step_dropin(self):
@@ -247,16 +248,19 @@ def run_ours(args, rank, world, local_rank):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    from rhseg_b200 import dist as rdist
+
     def exchange(result):
-        """The path's only cross-rank step: ONE all-reduce of loss + metric ratios' sources +
-        head/FiLM parameter gradients (tiny; pixel data never leaves its GPU)."""
+        """The path's only cross-rank step: ONE all-reduce of the packed step summary (loss terms,
+        valid-sample counts, confusion matrices; rhseg_b200.dist) + the head/FiLM parameter gradients
+        (a few thousand floats).  Pixel data never leaves its GPU."""
         if world == 1:
             return
-        scal, ratios = result
-        parts = [scal.reshape(-1).double()] + [r.flatten().double() for r in ratios]
-        parts += [g.flatten().double() for g in st.grads[len(st.feats):]]
-        buf = torch.cat(parts)
+        scal, _ratios = result
+        buf = torch.cat([rdist.pack_step_summary(scal, B, st.confusion)] +
+                        [g.flatten().double() for g in st.grads[len(st.feats):]])
         torch.distributed.all_reduce(buf)
+        st.global_summary = buf
 
     # ---- device-resident timing (`value`) ----
     for _ in range(max(args.warmup, 3)):
