@@ -129,7 +129,7 @@ class GpuStep:
         leaves = self.feats + [p for grp in self.params for p in grp]
         self.grads = torch.autograd.grad(out.loss, leaves)  # dfeats per level + head / FiLM parameter grads
         self.result = (out.scalars, out.ratios)
-        self.confusion = out.confusion
+        self.confusion, self.summary = out.confusion, out.summary
         return self.result
 
     def step_dropin(self):
@@ -256,9 +256,7 @@ def run_ours(args, rank, world, local_rank):
         (a few thousand floats).  Pixel data never leaves its GPU."""
         if world == 1:
             return
-        scal, _ratios = result
-        buf = torch.cat([rdist.pack_step_summary(scal, B, st.confusion)] +
-                        [g.flatten().double() for g in st.grads[len(st.feats):]])
+        buf = torch.cat([st.summary] + [g.reshape(-1).double() for g in st.grads[len(st.feats):]])
         torch.distributed.all_reduce(buf)
         st.global_summary = buf
 
@@ -277,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                st.step()
+                exchange(st.step())  # NCCL all-reduce is captured with the step (no host work per replay)
             g.replay()
             torch.cuda.synchronize()
             graph = g
@@ -289,7 +287,6 @@ def run_ours(args, rank, world, local_rank):
     def one_step():
         if graph is not None:
             graph.replay()
-            exchange(st.result)
         else:
             exchange(st.step())
 

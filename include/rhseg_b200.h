@@ -234,10 +234,13 @@ int rhseg_head_dz_fullres_fused(const float* logits, const float* targets, long 
  * level L, followed by each level's [5,nc_L] ratio block of rhseg_metric_ratios computed from the
  * workspace's confusion matrix; coef_all = the levels' [B,K_L,3] backward coefficients back to back.
  * weights_all = the levels' class weights back to back; K_per_level / groups_per_level are HOST
- * arrays (groups_per_level[0] is ignored).                                                  */
+ * arrays (groups_per_level[0] is ignored).  summary (optional, fp64 [2 + 4*n_levels + sum nc_L^2]):
+ * the ADDITIVE per-rank quantities a batch-sharded job all-reduces: B, consistency*B, per level
+ * (sum_b CE_b, sum_valid Dice_b, #valid dice samples, #non-NaN CE samples), then the confusion
+ * counts as fp64.                                                                           */
 int rhseg_step_finalize(const void* eval_words, const float* weights_all, int B, int n_levels,
                         const int32_t* K_per_level, const int32_t* groups_per_level, double smooth,
-                        long n_pix, float* out, float* coef_all, void* stream);
+                        long n_pix, float* out, float* coef_all, double* summary, void* stream);
 
 /* Fused per-level TRAINING evaluation (train.py:206-239 for one level in one pass): loss
  * statistics + train-path prediction + confusion matrix of the masked one-hot prediction +

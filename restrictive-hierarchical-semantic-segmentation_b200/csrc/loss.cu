@@ -208,7 +208,8 @@ __device__ __forceinline__ SampleLoss sample_loss(const double* __restrict__ st,
 // All levels in parallel: thread <-> (level, sample); shared-memory fp64 atomics per level.
 __global__ void __launch_bounds__(256)
 step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ weights, StepLevels lv, int B,
-                     double smooth, double inv_bn, float* __restrict__ out, float* __restrict__ coef) {
+                     double smooth, double inv_bn, float* __restrict__ out, float* __restrict__ coef,
+                     double* __restrict__ summary) {
   __shared__ double acc[RHSEG_MAX_LEVELS][4];  // ce_sum, dice_sum, n_dice, n_ce
   __shared__ size_t w_off[RHSEG_MAX_LEVELS + 1], k_off[RHSEG_MAX_LEVELS + 1], c_off[RHSEG_MAX_LEVELS + 1], r_off[RHSEG_MAX_LEVELS + 1];
   const int tid = threadIdx.x, nL = lv.n_levels;
@@ -278,6 +279,25 @@ step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ we
     const float consf = cons_count > 0 ? (float)(cons_total / (double)cons_count) : 0.f;
     out[0] = total + consf;
     out[1] = consf;
+    if (summary) {  // additive per-rank quantities for the data-parallel all-reduce (dist.py layout)
+      summary[0] = (double)B;
+      summary[1] = (double)consf * (double)B;
+      for (int L = 0; L < nL; ++L) {
+        summary[2 + 4 * L] = acc[L][0];
+        summary[3 + 4 * L] = acc[L][1];
+        summary[4 + 4 * L] = acc[L][2];
+        summary[5 + 4 * L] = acc[L][3];
+      }
+    }
+  }
+  if (summary) {  // confusion counts as fp64 (exact below 2^53), level after level
+    size_t s_off = 2 + 4 * (size_t)nL;
+    for (int L = 0; L < nL; ++L) {
+      const int K = lv.K[L], nc = lv.child[L] ? K + 1 : K;
+      const long long* conf = reinterpret_cast<const long long*>(ws + w_off[L] + (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K);
+      for (int i = tid; i < nc * nc; i += blockDim.x) summary[s_off + i] = (double)conf[i];
+      s_off += (size_t)nc * nc;
+    }
   }
 }
 
@@ -475,7 +495,7 @@ extern "C" int rhseg_consistency_sums(const float* cur, const float* prev, const
 
 extern "C" int rhseg_step_finalize(const void* eval_words, const float* weights_all, int B, int n_levels,
                                    const int32_t* K_per_level, const int32_t* groups_per_level, double smooth,
-                                   long n_pix, float* out, float* coef_all, void* stream) {
+                                   long n_pix, float* out, float* coef_all, double* summary, void* stream) {
   if (!eval_words || !weights_all || !K_per_level || !groups_per_level || !out || !coef_all) return RHSEG_ERR_ARG;
   if (B <= 0 || n_levels < 1 || n_levels > RHSEG_MAX_LEVELS || n_pix <= 0) return RHSEG_ERR_ARG;
   StepLevels lv{};
@@ -487,7 +507,7 @@ extern "C" int rhseg_step_finalize(const void* eval_words, const float* weights_
     lv.child[L] = L == 0 ? 0 : 1;
   }
   step_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(eval_words), weights_all, lv, B,
-                                                            smooth, 1.0 / ((double)B * (double)n_pix), out, coef_all);
+                                                            smooth, 1.0 / ((double)B * (double)n_pix), out, coef_all, summary);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }

@@ -63,6 +63,22 @@ def all_reduce_step_summary(scalars, batch_local, confusion, group=None):
     return unpack_global(buf, n, [tuple(c.shape) for c in confusion])
 
 
+def all_reduce_summary(summary: torch.Tensor, n_levels: int, conf_shapes, extra: Sequence[torch.Tensor] = (), group=None):
+    """Fused-step variant: `summary` is StepOutput.summary (already in the packed layout, written by
+    rhseg_step_finalize).  `extra` tensors (e.g. the head / FiLM parameter gradients) ride in the same
+    all-reduce.  Returns (global summary dict, reduced extras as fp64 views)."""
+    flat = [summary] + [e.reshape(-1).double() for e in extra]
+    buf = torch.cat(flat) if len(flat) > 1 else summary.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    out = unpack_global(buf, n_levels, conf_shapes)
+    views, off = [], summary.numel()
+    for e in extra:
+        views.append(buf[off:off + e.numel()].view(e.shape))
+        off += e.numel()
+    return out, views
+
+
 def dice_grad_scale(n_dice_local: torch.Tensor, n_dice_global: torch.Tensor, world_size: int) -> torch.Tensor:
     """Factor for a rank's Dice gradient so that DDP's mean over ranks equals the gradient of the
     single-process Dice (a mean over the GLOBAL count of valid samples): world * n_local / n_global.

@@ -29,9 +29,11 @@ _I32 = ctypes.c_int32
 
 class StepOutput:
     """Everything one training step reports, still on the device (no host sync)."""
-    __slots__ = ("loss", "scalars", "level_ce", "level_dice", "consistency", "confusion", "ratios", "probs", "logits")
+    __slots__ = ("loss", "scalars", "level_ce", "level_dice", "consistency", "confusion", "ratios", "probs", "logits",
+                 "summary")
 
-    def __init__(self, loss, scalars, confusion, ratios, probs, logits, n):
+    def __init__(self, loss, scalars, confusion, ratios, probs, logits, n, summary=None):
+        self.summary = summary                 # fp64 additive per-rank summary for dist.all_reduce_summary
         self.loss = loss                       # 0-dim, differentiable
         self.scalars = scalars                 # [2 + 4*n] fp32: total, consistency, then (ce, dice, n_dice, n_ce) per level
         self.consistency = scalars[1]
@@ -91,10 +93,11 @@ class _FusedStepFn(torch.autograd.Function):
         scal_all = torch.empty((2 + 4 * n + n_ratio,), dtype=torch.float32, device=dev)
         scalars = scal_all[:2 + 4 * n]
         coef_all = torch.empty((B * sum(tree.head_channels) * 3,), dtype=torch.float32, device=dev)
+        summary = torch.empty((2 + 4 * n + sum(o[3] * o[3] for o in offs),), dtype=torch.float64, device=dev)
         Ks = (_I32 * n)(*tree.head_channels)
         Gs = (_I32 * n)(*[tree.group_count(L) for L in range(n)])
         call("rhseg_step_finalize", ptr(ws), ptr(weights_all), B, n, Ks, Gs, float(smooth), n_pix, ptr(scal_all),
-             ptr(coef_all), st)
+             ptr(coef_all), ptr(summary), st)
         conf, ratios, r_off = [], [], 2 + 4 * n
         for L in range(n):
             nc = offs[L][3]
@@ -106,7 +109,7 @@ class _FusedStepFn(torch.autograd.Function):
         ctx.save_for_backward(target, coef_all, *r["feats"], *r["head_w"], *r["film_w"], *r["logits"], *r["probs"],
                               *r["psums"], *r["eff_ws"], *[g for g in r["gbs"] if g is not None])
         ctx.set_materialize_grads(False)
-        outs = (scalars[0], scalars) + tuple(conf) + tuple(ratios) + tuple(r["probs"]) + tuple(r["logits"])
+        outs = (scalars[0], scalars) + tuple(conf) + tuple(ratios) + tuple(r["probs"]) + tuple(r["logits"]) + (summary,)
         ctx.mark_non_differentiable(*outs[1:])
         return outs
 
@@ -211,4 +214,4 @@ class FusedHierStep:
         outs = _FusedStepFn.apply(self.tree, out_size, self.weights(feats[0].device), self.smooth, target,
                                   *feats, *head_w, *head_b, *film_w, *film_b)
         return StepOutput(outs[0], outs[1], list(outs[2:2 + n]), list(outs[2 + n:2 + 2 * n]),
-                          list(outs[2 + 2 * n:2 + 3 * n]), list(outs[2 + 3 * n:2 + 4 * n]), n)
+                          list(outs[2 + 2 * n:2 + 3 * n]), list(outs[2 + 3 * n:2 + 4 * n]), n, outs[2 + 4 * n])

@@ -125,3 +125,17 @@ def test_fused_step_full_size_hrnet_against_oracle_sample():
         close(leaves[0][L].grad, leaves_ref[0][L].grad, what=f"dfeats{L}")
         close(leaves[1][L].grad, leaves_ref[1][L].grad, rtol=2e-5, what=f"dhead_w{L}")
     close(leaves[3][0].grad, leaves_ref[3][0].grad, rtol=2e-5, what="dfilm_w0")
+
+
+def test_fused_step_summary_matches_pack_layout():
+    """StepOutput.summary (written by rhseg_step_finalize) == dist.pack_step_summary of the same step."""
+    from rhseg_b200 import dist as rdist
+    fx = Fixture("unet_tl_odd_notooth")
+    _, out, _ = _step(fx, requires_grad=False)
+    want = rdist.pack_step_summary(out.scalars, fx.B, out.confusion)
+    assert out.summary.shape == want.shape
+    close(out.summary, want, rtol=1e-6, what="summary")
+    glob, extras = rdist.all_reduce_summary(out.summary, fx.nL, [tuple(c.shape) for c in out.confusion], extra=[out.scalars])
+    assert abs(float(glob["total"]) - out.loss.item()) < 1e-5
+    assert torch.equal(glob["confusion"][1], out.confusion[1])
+    close(extras[0], out.scalars, rtol=1e-6, what="extra")
