@@ -102,6 +102,20 @@ int rhseg_head_level_fwd(const float* feats, const float* eff_w, const float* ef
                          float* z_lo, float* logits, float* probs, double* psum, int zero_psum,
                          void* stream);
 
+/* Level forward of an UPSAMPLED head (HRNet) fused with rhseg_level_eval: the hi-res pass that
+ * interpolates and activates the logits also evaluates them against the ternary targets while
+ * they are in registers.  Arguments = rhseg_head_level_fwd (psum must be zeroed by the caller) +
+ * rhseg_level_eval (child is derived from act_mode).  Returns RHSEG_ERR_UNSUPPORTED for heads at
+ * feature resolution: call the two functions separately there.                              */
+int rhseg_head_level_fwd_eval(const float* feats, const float* eff_w, const float* eff_b,
+                              const float* prev_probs, const int32_t* table,
+                              int B, int C, int Hf, int Wf, int H, int W, int K, int K_prev, int act_mode,
+                              float* z_lo, float* logits, float* probs, double* psum,
+                              const float* targets, long t_bstride, long t_cstride,
+                              const float* parent_targets, long pt_bstride, long pt_cstride,
+                              const unsigned char* prev_idx, void* out_words, unsigned char* idx_out,
+                              void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * (2') head, backward (what autograd does for the reference; closed forms in DESIGN.md).
  * --------------------------------------------------------------------------------------- */

@@ -157,7 +157,12 @@ struct LevelInfo {
 // are compared with the reference at 1e-5 relative, three orders of magnitude above that error,
 // and the kernels that evaluate them are instruction-bound otherwise.  Anything that decides an
 // INTEGER result (argmax of softmax) goes through argmax_softmax_aten() below instead.
-__device__ __forceinline__ float sigmoidf_ref(float z) { return __frcp_rn(1.0f + __expf(-z)); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoidf_ref(float z) { return rcp_approx(1.0f + __expf(-z)); }
 
 // Segmented (per contiguous group) softmax over K channels; groups start where start_mask has a bit.
 template <int K>
@@ -178,9 +183,9 @@ __device__ __forceinline__ void grouped_softmax(const float (&z)[K], int start_m
   for (int k = K - 2; k >= 0; --k) s[k] = ((start_mask >> (k + 1)) & 1) ? s[k] : s[k + 1];
   // one reciprocal per group (computed at the group's first channel, copied forward)
   float r[K];
-  r[0] = __frcp_rn(s[0]);
+  r[0] = rcp_approx(s[0]);
 #pragma unroll
-  for (int k = 1; k < K; ++k) r[k] = ((start_mask >> k) & 1) ? __frcp_rn(s[k]) : r[k - 1];
+  for (int k = 1; k < K; ++k) r[k] = ((start_mask >> k) & 1) ? rcp_approx(s[k]) : r[k - 1];
 #pragma unroll
   for (int k = 0; k < K; ++k) q[k] = e[k] * r[k];
 }
@@ -217,7 +222,7 @@ __device__ __forceinline__ void fast_softmax(const float (&z)[K], float (&p)[K],
   sum = 0.f;
 #pragma unroll
   for (int k = 0; k < K; ++k) { p[k] = __expf(z[k] - mx); sum += p[k]; }
-  const float inv = __frcp_rn(sum);
+  const float inv = rcp_approx(sum);
 #pragma unroll
   for (int k = 0; k < K; ++k) p[k] *= inv;
 }
@@ -231,23 +236,37 @@ __device__ __forceinline__ bool beats(float v, float best) { return (v > best) |
 // (exp(-d) must round to 1 or 1-ulp).  Only such near-ties (and non-finite inputs) take the slow
 // path that replays ATen's arithmetic: max, sequential sum of expf(z-max), IEEE division.
 template <int K>
+__device__ __noinline__ int argmax_softmax_slow(const float* zp) {
+  float z[K], p[K], mx, sum;
+#pragma unroll
+  for (int k = 0; k < K; ++k) z[k] = zp[k];
+  full_softmax<K>(z, p, mx, sum);
+  float best = p[0];
+  int idx = 0;
+#pragma unroll
+  for (int k = 1; k < K; ++k)
+    if (beats(p[k], best)) { best = p[k]; idx = k; }
+  return idx;
+}
+
+template <int K>
 __device__ __forceinline__ int argmax_softmax_aten(const float (&z)[K]) {
   float best = z[0];
   int idx = 0;
 #pragma unroll
   for (int k = 1; k < K; ++k)
     if (z[k] > best) { best = z[k]; idx = k; }
-  bool slow = !(fabsf(best) <= 3.0e38f);  // inf / NaN anywhere near the top
+  // second-largest logit (ties with the maximum included): a near-tie is the only way softmax rounding
+  // can move the argmax to an earlier channel
+  float second = -3.4e38f;
 #pragma unroll
-  for (int k = 0; k < K; ++k) slow |= (k != idx) && !(best - z[k] > 2.0e-6f);
-  if (slow) {
-    float p[K], mx, sum;
-    full_softmax<K>(z, p, mx, sum);
-    best = p[0];
-    idx = 0;
+  for (int k = 0; k < K; ++k) second = (k != idx) ? fmaxf(second, z[k]) : second;
+  const bool slow = !(best - second > 2.0e-6f) || !(fabsf(best) <= 3.0e38f);  // near-tie, inf or NaN
+  if (K > 1 && slow) {
+    float zl[K];
 #pragma unroll
-    for (int k = 1; k < K; ++k)
-      if (beats(p[k], best)) { best = p[k]; idx = k; }
+    for (int k = 0; k < K; ++k) zl[k] = z[k];
+    idx = argmax_softmax_slow<K>(zl);
   }
   return idx;
 }

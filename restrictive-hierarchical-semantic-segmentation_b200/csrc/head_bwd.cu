@@ -537,9 +537,9 @@ extern "C" int rhseg_head_conv_bwd(const float* feats, const float* dz, const fl
     }
     if constexpr (KK == 4) {
       const int t = tune_env("RHSEG_TUNE_BWD_S1");
-      if (t == 1) return launch_conv_bwd<KK, 1, 2, PipeCfg<8, 8, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
-      if (t == 2) return launch_conv_bwd<KK, 1, 4, PipeCfg<4, 8, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
-      if (t == 3) return launch_conv_bwd<KK, 1, 2, PipeCfg<8, 16, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+      if (t == 1) return launch_conv_bwd<KK, 1, 2, PipeCfg<8, 8, 4>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+      if (t == 2) return launch_conv_bwd<KK, 1, 4, PipeCfg<4, 8, 4>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+      if (t == 3) return launch_conv_bwd<KK, 1, 4, PipeCfg<8, 16, 2>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
     }
     return launch_conv_bwd<KK, 1, (KK <= 4 ? 4 : 2), BwdCfgS1>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
   });

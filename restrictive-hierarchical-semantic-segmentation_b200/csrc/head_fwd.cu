@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "pipeline.cuh"
+#include "eval_accum.cuh"
 
 namespace rhseg {
 
@@ -468,87 +469,130 @@ upsample_act_kernel(const float* __restrict__ z_lo, const float* __restrict__ pr
 // 16 x (16*VEC) hi-res tile, stages the low-res logit patch it reads in shared memory and
 // interpolates from there (shared-memory loads with immediate offsets instead of 64 global loads
 // with 64-bit address arithmetic per thread).
-template <int K, int VEC, int MODE>
-__global__ void __launch_bounds__(256)
+// EVAL: additionally run the per-level training evaluation (eval_accum.cuh) on the pixels while their
+// logits are in registers: statistics, prediction index map, confusion matrix, consistency sums.
+struct EvalArgs {
+  const float* targets;
+  long t_bstride, t_cstride;
+  const float* parent_targets;
+  long pt_bstride, pt_cstride;
+  const unsigned char* prev_idx;
+  int child;
+  double* stats;
+  double* cons;
+  unsigned long long* conf;
+  unsigned char* idx_out;
+};
+
+template <int K, int VEC, int MODE, bool EVAL>
+__global__ void __launch_bounds__(256, 2)
 upsample_act_tiled_kernel(const float* __restrict__ z_lo, const float* __restrict__ prev_probs,
                           const int32_t* __restrict__ table, int Hf, int Wf, int H, int W, int K_prev, float sy,
-                          float sx, float* __restrict__ logits, float* __restrict__ probs, double* __restrict__ psum) {
+                          float sx, int tiles_x, int tiles_per_sample, float* __restrict__ logits,
+                          float* __restrict__ probs, double* __restrict__ psum, EvalArgs ea) {
   constexpr int TH = 16, TW = 16 * VEC;
   constexpr int PH = TH + 2, PW = TW + 2;  // patch bound for scale <= 1
   __shared__ float patch[K][PH][PW];
   __shared__ float red[8 * K];
-  const int b = blockIdx.z, tid = threadIdx.x;
-  const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
-  const int ylast = min(ty0 + TH, H) - 1, xlast = min(tx0 + TW, W) - 1;
-  const int r0 = (int)(sy * (float)ty0), c0 = (int)(sx * (float)tx0);
-  const int r1 = min((int)(sy * (float)ylast) + 1, Hf - 1), c1 = min((int)(sx * (float)xlast) + 1, Wf - 1);
-  const int ph = r1 - r0 + 1, pw = c1 - c0 + 1;
-  const long N = (long)H * W, Nf = (long)Hf * Wf;
-  {
-    const float* zb = z_lo + (size_t)b * K * Nf;
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int kr = warp; kr < K * ph; kr += 8) {
-      const int k = kr / ph, rr = kr - k * ph;
-      const float* src = zb + (size_t)k * Nf + (size_t)(r0 + rr) * Wf + c0;
-      for (int cc = lane; cc < pw; cc += 32) patch[k][rr][cc] = __ldg(src + cc);
-    }
-  }
-  __syncthreads();
-  const int y = ty0 + (tid >> 4), x0 = tx0 + (tid & 15) * VEC;
-  const bool ok = y < H && x0 < W;  // W % VEC == 0 guaranteed by the launcher
+  __shared__ float ered[EVAL ? 8 * EvalAccum<K>::NACC : 1];
+  __shared__ int hist[EVAL ? (K + 1) * (K + 1) : 1];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  EvalAccum<K> ev;
+  if constexpr (EVAL)
+    ev.init(ea.child, ea.child && ea.prev_idx != nullptr && ea.parent_targets != nullptr, table, hist, 256);
   const LevelInfo li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? table : nullptr);
-  const long px = (long)y * W + x0;
-  float z[K][VEC], pp[K][VEC], prob[K][VEC];
-  if (ok) {
-    const Lerp ly = make_lerp(y, sy, Hf);
-    const int row0 = (ly.i0 - r0) * PW, row1 = (ly.i1 - r0) * PW;
-    const float* pbase = &patch[0][0][0];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const Lerp lx = make_lerp(x0 + v, sx, Wf);
-      const float* p00 = pbase + row0 + (lx.i0 - c0);
-      const float* p01 = pbase + row0 + (lx.i1 - c0);
-      const float* p10 = pbase + row1 + (lx.i0 - c0);
-      const float* p11 = pbase + row1 + (lx.i1 - c0);
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-        z[k][v] = ly.l0 * (lx.l0 * p00[k * PH * PW] + lx.l1 * p01[k * PH * PW]) +
-                  ly.l1 * (lx.l0 * p10[k * PH * PW] + lx.l1 * p11[k * PH * PW]);
-    }
-    if constexpr (MODE == RHSEG_ACT_GROUPED) {
-      const float* pb = prev_probs + (size_t)b * K_prev * N;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if ((li.start_mask >> k) & 1) {
-          const Vec<VEC> t = ld_cached<VEC>(pb + (size_t)li.parent[k] * N + px);
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) pp[k][v] = t.v[v];
-        } else {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) pp[k][v] = pp[k > 0 ? k - 1 : 0][v];
-        }
-      }
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) { z[k][v] = 0.f; pp[k][v] = 0.f; }
-  }
-  activate<K, VEC, MODE>(z, pp, li.start_mask, prob);
+  const long N = (long)H * W, Nf = (long)Hf * Wf;
+  const float* zb = z_lo + (size_t)b * K * Nf;
   float ps[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    ps[k] = 0.f;
-    if (ok) {
-      Vec<VEC> zo, po;
+  for (int k = 0; k < K; ++k) ps[k] = 0.f;
+
+  // persistent over the sample's tiles: pool sums / evaluation statistics are reduced once per CTA
+  for (int tile = blockIdx.x; tile < tiles_per_sample; tile += gridDim.x) {
+    const int ty0 = (tile / tiles_x) * TH, tx0 = (tile % tiles_x) * TW;
+    const int ylast = min(ty0 + TH, H) - 1, xlast = min(tx0 + TW, W) - 1;
+    const int r0 = (int)(sy * (float)ty0), c0 = (int)(sx * (float)tx0);
+    const int r1 = min((int)(sy * (float)ylast) + 1, Hf - 1), c1 = min((int)(sx * (float)xlast) + 1, Wf - 1);
+    const int ph = r1 - r0 + 1, pw = c1 - c0 + 1;
+    __syncthreads();  // previous tile's readers are done with the patch
+    {
+      const int lane = tid & 31, warp = tid >> 5;
+      for (int rr = warp; rr < ph; rr += 8)
+        for (int cc = lane; cc < pw; cc += 32) {
+          const float* src = zb + (size_t)(r0 + rr) * Wf + c0 + cc;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) { zo.v[v] = z[k][v]; po.v[v] = prob[k][v]; ps[k] += po.v[v]; }
-      *reinterpret_cast<Vec<VEC>*>(logits + ((size_t)b * K + k) * N + px) = zo;
-      *reinterpret_cast<Vec<VEC>*>(probs + ((size_t)b * K + k) * N + px) = po;
+          for (int k = 0; k < K; ++k) patch[k][rr][cc] = __ldg(src + (size_t)k * Nf);
+        }
+    }
+    __syncthreads();
+    const int y = ty0 + (tid >> 4), x0 = tx0 + (tid & 15) * VEC;
+    const bool ok = y < H && x0 < W;  // W % VEC == 0 guaranteed by the launcher
+    const long px = (long)y * W + x0;
+    float z[K][VEC], pp[K][VEC], prob[K][VEC];
+    if (ok) {
+      const Lerp ly = make_lerp(y, sy, Hf);
+      const int row0 = (ly.i0 - r0) * PW, row1 = (ly.i1 - r0) * PW;
+      const float* pbase = &patch[0][0][0];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const Lerp lx = make_lerp(x0 + v, sx, Wf);
+        const float* p00 = pbase + row0 + (lx.i0 - c0);
+        const float* p01 = pbase + row0 + (lx.i1 - c0);
+        const float* p10 = pbase + row1 + (lx.i0 - c0);
+        const float* p11 = pbase + row1 + (lx.i1 - c0);
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          z[k][v] = ly.l0 * (lx.l0 * p00[k * PH * PW] + lx.l1 * p01[k * PH * PW]) +
+                    ly.l1 * (lx.l0 * p10[k * PH * PW] + lx.l1 * p11[k * PH * PW]);
+      }
+      if constexpr (MODE == RHSEG_ACT_GROUPED) {
+        const float* pb = prev_probs + (size_t)b * K_prev * N;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if ((li.start_mask >> k) & 1) {
+            const Vec<VEC> t = ld_cached<VEC>(pb + (size_t)li.parent[k] * N + px);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) pp[k][v] = t.v[v];
+          } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) pp[k][v] = pp[k > 0 ? k - 1 : 0][v];
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { z[k][v] = 0.f; pp[k][v] = 0.f; }
+    }
+    activate<K, VEC, MODE>(z, pp, li.start_mask, prob);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (ok) {
+        Vec<VEC> zo, po;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { zo.v[v] = z[k][v]; po.v[v] = prob[k][v]; ps[k] += po.v[v]; }
+        *reinterpret_cast<Vec<VEC>*>(logits + ((size_t)b * K + k) * N + px) = zo;
+        *reinterpret_cast<Vec<VEC>*>(probs + ((size_t)b * K + k) * N + px) = po;
+      }
+    }
+    if constexpr (EVAL) {
+      float t[K][VEC], ptv[K][VEC];
+      unsigned char pidx[VEC], my_idx[VEC];
+      ev.template load_targets<VEC>(ea.targets, ea.t_bstride, ea.t_cstride, ea.parent_targets, ea.pt_bstride, ea.pt_cstride,
+                                    ea.prev_idx, b, N, px, ok, t, ptv, pidx);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float zz[K], tt[K], pt[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { zz[k] = z[k][v]; tt[k] = t[k][v]; pt[k] = ptv[k][v]; }
+        my_idx[v] = (unsigned char)ev.pixel(zz, tt, pt, pidx[v], ok);
+      }
+      ev.template store_idx<VEC>(ea.idx_out, b, N, px, ok, my_idx);
     }
   }
   block_psum<K, 8>(ps, psum + (size_t)b * K, red, [] { __syncthreads(); });
+  if constexpr (EVAL) ev.template finish<8>(ered, hist, ea.stats, ea.cons, ea.conf, table, b);
 }
 
 template <int K, int VEC, int J, int MODE, typename CFG>
@@ -609,21 +653,34 @@ static int fwd_fullres(const float* feats, const float* eff_w, const float* eff_
 
 template <int K, int MODE>
 static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32_t* table, int B, int Hf, int Wf,
-                         int H, int W, int K_prev, float* logits, float* probs, double* psum, cudaStream_t st) {
+                         int H, int W, int K_prev, float* logits, float* probs, double* psum, cudaStream_t st,
+                         const EvalArgs* ea = nullptr) {
   const float sy = H > 1 ? (float)(Hf - 1) / (float)(H - 1) : 0.f;
   const float sx = W > 1 ? (float)(Wf - 1) / (float)(W - 1) : 0.f;
   constexpr int THREADS = 256;
   if (sy <= 1.0f && sx <= 1.0f) {  // upsampling: tiled kernel
-    if (W % 4 == 0) {
-      dim3 grid((W + 63) / 64, (H + 15) / 16, B);
-      upsample_act_tiled_kernel<K, 4, MODE><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, logits, probs, psum);
+    auto al4 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; };
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    bool v4 = W % 4 == 0;
+    if (ea) v4 = v4 && al16(ea->targets) && ea->t_bstride % 4 == 0 && ea->t_cstride % 4 == 0 && al4(ea->prev_idx) && al4(ea->idx_out) &&
+                 (!ea->parent_targets || (al16(ea->parent_targets) && ea->pt_bstride % 4 == 0 && ea->pt_cstride % 4 == 0));
+    const EvalArgs none{};
+    const int slots = std::max(1, device_sm_count() * 2 / B);  // CTAs per sample: one resident wave at 2 CTAs/SM
+    if (v4) {
+      const int tiles_x = (W + 63) / 64, tiles = tiles_x * ((H + 15) / 16);
+      dim3 grid(std::min(slots, tiles), B);
+      if (ea) upsample_act_tiled_kernel<K, 4, MODE, true><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
+      else upsample_act_tiled_kernel<K, 4, MODE, false><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
     } else {
-      dim3 grid((W + 15) / 16, (H + 15) / 16, B);
-      upsample_act_tiled_kernel<K, 1, MODE><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, logits, probs, psum);
+      const int tiles_x = (W + 15) / 16, tiles = tiles_x * ((H + 15) / 16);
+      dim3 grid(std::min(slots, tiles), B);
+      if (ea) upsample_act_tiled_kernel<K, 1, MODE, true><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
+      else upsample_act_tiled_kernel<K, 1, MODE, false><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
     }
     RHSEG_LAUNCH_CHECK();
     return RHSEG_OK;
   }
+  if (ea) return RHSEG_ERR_UNSUPPORTED;  // fused evaluation exists for upsampling heads only
   if (W % 4 == 0) {
     const int vps = H * (W / 4);
     dim3 grid((vps + THREADS - 1) / THREADS, B);
@@ -660,10 +717,10 @@ extern "C" int rhseg_film_fold(const float* head_w, const float* head_b, const f
   return RHSEG_OK;
 }
 
-extern "C" int rhseg_head_level_fwd(const float* feats, const float* eff_w, const float* eff_b,
-                                    const float* prev_probs, const int32_t* table, int B, int C, int Hf, int Wf,
-                                    int H, int W, int K, int K_prev, int act_mode, float* z_lo, float* logits,
-                                    float* probs, double* psum, int zero_psum, void* stream) {
+static int level_fwd_impl(const float* feats, const float* eff_w, const float* eff_b,
+                          const float* prev_probs, const int32_t* table, int B, int C, int Hf, int Wf,
+                          int H, int W, int K, int K_prev, int act_mode, float* z_lo, float* logits,
+                          float* probs, double* psum, int zero_psum, void* stream, const EvalArgs* ea) {
   if (!feats || !eff_w || !eff_b || !logits || !probs || !psum) return RHSEG_ERR_ARG;
   if (B <= 0 || C <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
@@ -672,6 +729,7 @@ extern "C" int rhseg_head_level_fwd(const float* feats, const float* eff_w, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (zero_psum) RHSEG_CUDA(cudaMemsetAsync(psum, 0, sizeof(double) * B * K, st));
   const bool up = (H != Hf) || (W != Wf);
+  if (ea && !up) return RHSEG_ERR_UNSUPPORTED;
   const int Nf = Hf * Wf;
   if (!up) {
     RHSEG_DISPATCH_K(K, {
@@ -691,9 +749,9 @@ extern "C" int rhseg_head_level_fwd(const float* feats, const float* eff_w, cons
       int t = 0;
       if constexpr (KK == 4) t = tune_env("RHSEG_TUNE_FWD_S1");
       if constexpr (KK == 4) {
-        if (t == 1) rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, PipeCfg<4, 16, 4, 1>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
-        else if (t == 2) rc = launch_fwd<KK, 1, 1, MODE_CONV_ONLY, PipeCfg<8, 16, 4, 2>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
-        else if (t == 3) rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, PipeCfg<4, 8, 6, 2>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
+        if (t == 1) rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, PipeCfg<8, 16, 3, 2>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
+        else if (t == 2) rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, PipeCfg<8, 8, 4, 2>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
+        else if (t == 3) rc = launch_fwd<KK, 1, 4, MODE_CONV_ONLY, PipeCfg<4, 16, 4, 1>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
         else rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, FwdCfgS1>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
       } else {
         rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, FwdCfgS1>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
@@ -701,10 +759,39 @@ extern "C" int rhseg_head_level_fwd(const float* feats, const float* eff_w, cons
     }
     if (rc != RHSEG_OK) return rc;
     if (act_mode == RHSEG_ACT_SIGMOID)
-      return fwd_upsampled<KK, RHSEG_ACT_SIGMOID>(z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, logits, probs, psum, st);
+      return fwd_upsampled<KK, RHSEG_ACT_SIGMOID>(z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, logits, probs, psum, st, ea);
     if (act_mode == RHSEG_ACT_GROUPED)
-      return fwd_upsampled<KK, RHSEG_ACT_GROUPED>(z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, logits, probs, psum, st);
-    return fwd_upsampled<KK, RHSEG_ACT_ZEROS>(z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, logits, probs, psum, st);
+      return fwd_upsampled<KK, RHSEG_ACT_GROUPED>(z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, logits, probs, psum, st, ea);
+    return fwd_upsampled<KK, RHSEG_ACT_ZEROS>(z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, logits, probs, psum, st, ea);
   });
   return RHSEG_OK;
+}
+
+extern "C" int rhseg_head_level_fwd(const float* feats, const float* eff_w, const float* eff_b,
+                                    const float* prev_probs, const int32_t* table, int B, int C, int Hf, int Wf,
+                                    int H, int W, int K, int K_prev, int act_mode, float* z_lo, float* logits,
+                                    float* probs, double* psum, int zero_psum, void* stream) {
+  return level_fwd_impl(feats, eff_w, eff_b, prev_probs, table, B, C, Hf, Wf, H, W, K, K_prev, act_mode, z_lo, logits, probs,
+                        psum, zero_psum, stream, nullptr);
+}
+
+extern "C" int rhseg_head_level_fwd_eval(const float* feats, const float* eff_w, const float* eff_b,
+                                         const float* prev_probs, const int32_t* table, int B, int C, int Hf, int Wf,
+                                         int H, int W, int K, int K_prev, int act_mode, float* z_lo, float* logits,
+                                         float* probs, double* psum, const float* targets, long t_bstride,
+                                         long t_cstride, const float* parent_targets, long pt_bstride, long pt_cstride,
+                                         const unsigned char* prev_idx, void* out_words, unsigned char* idx_out,
+                                         void* stream) {
+  if (!targets || !out_words) return RHSEG_ERR_ARG;
+  if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  const int child = act_mode == RHSEG_ACT_SIGMOID ? 0 : 1;
+  const int nc = child ? K + 1 : K;
+  const size_t words = (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K + (size_t)nc * nc;
+  RHSEG_CUDA(cudaMemsetAsync(out_words, 0, words * 8, (cudaStream_t)stream));
+  double* stats = reinterpret_cast<double*>(out_words);
+  double* cons = stats + (size_t)B * K * RHSEG_NSTAT;
+  EvalArgs ea{targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, child, stats, cons,
+              reinterpret_cast<unsigned long long*>(cons + RHSEG_MAX_K), idx_out};
+  return level_fwd_impl(feats, eff_w, eff_b, prev_probs, table, B, C, Hf, Wf, H, W, K, K_prev, act_mode, z_lo, logits, probs,
+                        psum, 0, stream, &ea);
 }

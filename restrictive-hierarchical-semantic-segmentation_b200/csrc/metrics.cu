@@ -3,81 +3,15 @@
 // (train.py:206-231, predictEval.py:409-422).
 #include <algorithm>
 #include "common.cuh"
+#include "eval_accum.cuh"
 
 namespace rhseg {
-
-// class index of one pixel following ProcessClasses (performance_metrics.py:31-47)
-template <int K>
-__device__ __forceinline__ int process_class(const float (&x)[K], bool child) {
-  if (child) {
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) sum += x[k];
-    float best = (sum == 0.f) ? 1.0f : 0.0f;  // prepended "nothing positive" channel
-    int idx = 0;
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-      if (beats(x[k], best)) { best = x[k]; idx = k + 1; }
-    return idx;
-  }
-  float best = x[0];
-  int idx = 0;
-#pragma unroll
-  for (int k = 1; k < K; ++k)
-    if (beats(x[k], best)) { best = x[k]; idx = k; }
-  return idx;
-}
 
 // argmax(softmax(z)) with ATen's op order (train.py:219-221)
 template <int K>
 __device__ __forceinline__ int argmax_softmax(const float (&z)[K]) {
   return argmax_softmax_aten<K>(z);
 }
-
-// Warp-cooperative confusion counting without atomics or match: every lane owns up to SLOTS
-// cells (cell = lane + 32*slot) and counts, from 2*nc ballots, how many lanes of the warp hold
-// (target class a, predicted class b).  tc < 0 marks an ignored pixel.
-template <int NCMAX>
-struct WarpConfusion {
-  static constexpr int SLOTS = (NCMAX * NCMAX + 31) / 32;
-  int cnt[SLOTS];
-  int my_a[SLOTS], my_b[SLOTS];
-  __device__ __forceinline__ void init(int nc) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      const int cell = lane + 32 * s;
-      cnt[s] = 0;
-      my_a[s] = cell < nc * nc ? cell / nc : -2;
-      my_b[s] = cell < nc * nc ? cell % nc : -2;
-    }
-  }
-  __device__ __forceinline__ void add(int tc, int pc) {
-    unsigned ma[SLOTS], mb[SLOTS];
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) { ma[s] = 0u; mb[s] = 0u; }
-#pragma unroll
-    for (int c = 0; c < NCMAX; ++c) {
-      const unsigned ta = __ballot_sync(0xffffffffu, tc == c);
-      const unsigned pb = __ballot_sync(0xffffffffu, pc == c);
-#pragma unroll
-      for (int s = 0; s < SLOTS; ++s) {
-        if (my_a[s] == c) ma[s] = ta;
-        if (my_b[s] == c) mb[s] = pb;
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) cnt[s] += __popc(ma[s] & mb[s]);
-  }
-  __device__ __forceinline__ void flush(int* hist, int nc) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      const int cell = lane + 32 * s;
-      if (cell < nc * nc && cnt[s]) atomicAdd(&hist[cell], cnt[s]);
-    }
-  }
-};
 
 // warp-aggregated histogram update: lanes holding the same cell elect one leader
 __device__ __forceinline__ void hist_add(int* hist, int cell) {
@@ -220,140 +154,39 @@ level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ ta
                   const unsigned char* __restrict__ prev_idx, const int32_t* __restrict__ table, long N, int child,
                   double* __restrict__ stats, double* __restrict__ cons, unsigned long long* __restrict__ conf,
                   unsigned char* __restrict__ idx_out) {
-  constexpr int NS = RHSEG_NSTAT;
-  constexpr int NWARP = THREADS / 32;
-  constexpr int NACC = K * NS + K;  // statistics + one consistency accumulator per (group start) channel
-  __shared__ float red[NWARP][NACC];
+  __shared__ float red[THREADS / 32][EvalAccum<K>::NACC];
   __shared__ int hist[(K + 1) * (K + 1)];
-  const int nc = child ? K + 1 : K;
   const int b = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < nc * nc; i += THREADS) hist[i] = 0;
-  __syncthreads();
-  const bool do_cons = child && prev_idx != nullptr && parent_targets != nullptr;
-  const LevelInfo li = load_level_info<K>(child ? table : nullptr);
-  WarpConfusion<K + 1> wc;
-  wc.init(nc);
-  float a[K][NS], ca[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    ca[k] = 0.f;
-#pragma unroll
-    for (int j = 0; j < NS; ++j) a[k][j] = 0.f;
-  }
+  EvalAccum<K> ev;
+  ev.init(child, child && prev_idx != nullptr && parent_targets != nullptr, table, hist, THREADS);
   const float* zb = logits + (size_t)b * K * N;
-  const float* tb = targets + (size_t)b * t_bstride;
   // persistent over the sample's pixel vectors: one resident wave, statistics reduced once per CTA
   for (long px0 = (long)blockIdx.x * (THREADS * VEC); px0 < N; px0 += (long)gridDim.x * (THREADS * VEC)) {
     const long px = px0 + (long)tid * VEC;
     const bool ok = px < N;
     float z[K][VEC], t[K][VEC], ptv[K][VEC];
-    unsigned char pidx[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) pidx[v] = 0;
+    unsigned char pidx[VEC], my_idx[VEC];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      Vec<VEC> zv, tv;
+      Vec<VEC> zv;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) { zv.v[v] = 0.f; tv.v[v] = -1.f; ptv[k][v] = -1.f; }
-      if (ok) {
-        zv = ld_cached<VEC>(zb + (size_t)k * N + px);
-        tv = ld_cached<VEC>(tb + (size_t)k * t_cstride + px);
-        if (do_cons && ((li.start_mask >> k) & 1)) {
-          const Vec<VEC> pv = ld_cached<VEC>(parent_targets + (size_t)b * pt_bstride + (size_t)li.parent[k] * pt_cstride + px);
+      for (int v = 0; v < VEC; ++v) zv.v[v] = 0.f;
+      if (ok) zv = ld_cached<VEC>(zb + (size_t)k * N + px);
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) ptv[k][v] = pv.v[v];
-        }
-      }
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) { z[k][v] = zv.v[v]; t[k][v] = tv.v[v]; }
+      for (int v = 0; v < VEC; ++v) z[k][v] = zv.v[v];
     }
-    if (ok && do_cons) {
-      if constexpr (VEC == 4) {
-        const uchar4 q = *reinterpret_cast<const uchar4*>(prev_idx + (size_t)b * N + px);
-        pidx[0] = q.x; pidx[1] = q.y; pidx[2] = q.z; pidx[3] = q.w;
-      } else {
-        pidx[0] = prev_idx[(size_t)b * N + px];
-      }
-    }
-    unsigned char my_idx[VEC];
+    ev.template load_targets<VEC>(targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, b, N, px,
+                                  ok, t, ptv, pidx);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      float zz[K], p[K], mx, sum;
+      float zz[K], tt[K], pt[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) zz[k] = z[k][v];
-      fast_softmax<K>(zz, p, mx, sum);
-      const float lse = __logf(sum);
-      const int idx = argmax_softmax_aten<K>(zz);  // train.py:219-221, bit-exact
-      my_idx[v] = (unsigned char)idx;
-      float pr[K], et[K];
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const float tk = t[k][v];
-        const bool m = tk != -1.0f;
-        if (m && ok) {
-          const float lp = (zz[k] - mx) - lse;
-          a[k][0] = fmaf(tk, lp, a[k][0]);
-          a[k][1] += 1.0f;
-          a[k][2] = fmaf(p[k], tk, a[k][2]);
-          a[k][3] += p[k];
-          a[k][4] += tk;
-        }
-        pr[k] = (k == idx && m) ? 1.0f : 0.0f;
-        et[k] = m ? tk : 0.0f;
-      }
-      {
-        // ProcessClasses of the masked one-hot prediction: the predicted channel if its target is
-        // not ignored, otherwise "nothing positive" (class 0 on child levels, argmax of zeros = 0 else)
-        float pm = 0.f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) pm += pr[k];
-        const int pc = pm != 0.f ? (child ? idx + 1 : idx) : 0;
-        int tc = process_class<K>(et, child != 0);
-        if (!ok || (child && tc == 0)) tc = -1;  // out of range / torchmetrics ignore_index=0 on child levels
-        wc.add(tc, pc);
-      }
-      if (do_cons && ok) {
-        float gs[K];
-        group_sum<K>(pr, li.start_mask, gs);  // children one-hots summed per group
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-          if ((li.start_mask >> k) & 1) {
-            const float parent_hot = ((int)pidx[v] == li.parent[k] && ptv[k][v] != -1.0f) ? 1.0f : 0.0f;
-            ca[k] += fabsf(gs[k] - parent_hot);
-          }
-      }
+      for (int k = 0; k < K; ++k) { zz[k] = z[k][v]; tt[k] = t[k][v]; pt[k] = ptv[k][v]; }
+      my_idx[v] = (unsigned char)ev.pixel(zz, tt, pt, pidx[v], ok);
     }
-    if (ok && idx_out) {
-      if constexpr (VEC == 4) {
-        *reinterpret_cast<uchar4*>(idx_out + (size_t)b * N + px) = make_uchar4(my_idx[0], my_idx[1], my_idx[2], my_idx[3]);
-      } else {
-        idx_out[(size_t)b * N + px] = my_idx[0];
-      }
-    }
+    ev.template store_idx<VEC>(idx_out, b, N, px, ok, my_idx);
   }
-  const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-#pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      const float v = warp_sum(a[k][j]);
-      if (lane == 0) red[warp][k * NS + j] = v;
-    }
-    const float c = warp_sum(ca[k]);
-    if (lane == 0) red[warp][K * NS + k] = c;
-  }
-  __syncthreads();
-  if (tid < NACC) {
-    double acc = 0.0;
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) acc += (double)red[w][tid];
-    if (tid < K * NS) atomicAdd(&stats[(size_t)b * K * NS + tid], acc);
-    else if (do_cons && ((li.start_mask >> (tid - K * NS)) & 1)) atomicAdd(&cons[table[RHSEG_TBL_GROUP_OF + tid - K * NS]], acc);
-  }
-  wc.flush(hist, nc);
-  __syncthreads();
-  for (int i = tid; i < nc * nc; i += THREADS)
-    if (hist[i]) atomicAdd(&conf[i], (unsigned long long)hist[i]);
+  ev.template finish<THREADS / 32>(&red[0][0], hist, stats, cons, conf, table, b);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -58,37 +58,38 @@ class _FusedStepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tree: ClassTree, out_size, weights_all, smooth, target, *tensors):
         n = tree.num_levels
-        r = forward_levels(tree, out_size, tensors)
-        B, C, Hf, Wf, H, W = r["dims"]
-        dev = r["feats"][0].device
-        st = stream_of(r["feats"][0])
-        tables = tree.device_tables(dev)
-        n_pix = H * W
         native.require_cuda(target)
         if target.dtype != torch.float32:
             target = target.float()
-        if target.dim() != 4 or target.shape[0] != B or target.shape[1] != sum(tree.head_channels) \
-                or tuple(target.shape[2:]) != (H, W):
-            raise native.NativeError("target must be [B, sum(K_L), H, W] = [%d,%d,%d,%d], got %s"
-                                     % (B, sum(tree.head_channels), H, W, tuple(target.shape)))
-        if not (target.stride(3) == 1 and target.stride(2) == W):
+        if target.dim() != 4 or target.shape[1] != sum(tree.head_channels):
+            raise native.NativeError("target must be [B, sum(K_L), H, W] with sum(K_L) = %d, got %s"
+                                     % (sum(tree.head_channels), tuple(target.shape)))
+        if not (target.stride(3) == 1 and target.stride(2) == target.shape[3]):
             target = target.contiguous()
+        dev = target.device
+        B = target.shape[0]
         t_bs, t_cs = target.stride(0), target.stride(1)
-        # ---- evaluation: one pass per level ----
-        offs, words = _eval_layout(tree, B)
-        ws = torch.empty((words,), dtype=torch.float64, device=dev)
-        idx_maps = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) if L < n - 1 else None for L in range(n)]
+        esz = target.element_size()
         ch_off = [0]
         for k in tree.head_channels:
             ch_off.append(ch_off[-1] + k)
-        esz = target.element_size()
-        for L in range(n):
-            K = tree.head_channels[L]
-            t_ptr = target.data_ptr() + ch_off[L] * t_cs * esz
-            pt_ptr = target.data_ptr() + ch_off[L - 1] * t_cs * esz if L > 0 else None
-            call("rhseg_level_eval", ptr(r["logits"][L]), t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs,
-                 ptr(idx_maps[L - 1]) if L > 0 else None, ptr(tables[L]), B, K, n_pix, 1 if L > 0 else 0,
-                 ws.data_ptr() + offs[L][0] * 8, ptr(idx_maps[L]), st)
+        offs, words = _eval_layout(tree, B)
+        ws = torch.empty((words,), dtype=torch.float64, device=dev)
+        idx_maps = [torch.empty((B,) + tuple(target.shape[2:]), dtype=torch.uint8, device=dev) if L < n - 1 else None
+                    for L in range(n)]
+
+        def evaluate(L, dims):
+            if dims[0] != B or (dims[4], dims[5]) != tuple(target.shape[2:]):
+                raise native.NativeError("target %s does not match the head output [%d, *, %d, %d]"
+                                         % (tuple(target.shape), dims[0], dims[4], dims[5]))
+            return (target.data_ptr() + ch_off[L] * t_cs * esz, t_bs, t_cs,
+                    target.data_ptr() + ch_off[L - 1] * t_cs * esz if L > 0 else None,
+                    ptr(idx_maps[L - 1]) if L > 0 else None, ws.data_ptr() + offs[L][0] * 8, ptr(idx_maps[L]))
+
+        r = forward_levels(tree, out_size, tensors, evaluate)
+        B, C, Hf, Wf, H, W = r["dims"]
+        st = stream_of(r["feats"][0])
+        n_pix = H * W
         n_ratio = sum(5 * o[3] for o in offs)
         scal_all = torch.empty((2 + 4 * n + n_ratio,), dtype=torch.float32, device=dev)
         scalars = scal_all[:2 + 4 * n]

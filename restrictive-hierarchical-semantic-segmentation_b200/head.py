@@ -24,10 +24,13 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
-def forward_levels(tree: ClassTree, out_size, tensors):
+def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
     """Runs the per-level forward kernels.  `tensors` = feats[n] + head_w[n] + head_b[n] + film_w[n-1] +
     film_b[n-1].  Returns a dict with the inputs (contiguous fp32) and probs / logits / psums / eff_w /
-    gamma_beta per level plus the shape tuple."""
+    gamma_beta per level plus the shape tuple.
+    `evaluate(L, dims)` (fused training step) returns the rhseg_level_eval arguments of level L:
+    (targets_ptr, t_bs, t_cs, parent_ptr, prev_idx_ptr, out_words_ptr, idx_out_ptr); the evaluation then runs
+    inside the hi-res forward kernel (upsampled heads) or right after the level's forward (feature-resolution heads)."""
     n = tree.num_levels
     feats = [_f32c(t) for t in tensors[0:n]]
     head_w = [_f32c(t) for t in tensors[n:2 * n]]
@@ -67,9 +70,21 @@ def forward_levels(tree: ClassTree, out_size, tensors):
         psum = psum_all[psum_off:psum_off + B * K].view(B, K)
         psum_off += B * K
         z_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev) if upsampled else None
-        call("rhseg_head_level_fwd", ptr(f), ptr(eff_w), ptr(eff_b),
-             ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
-             B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum), 0, st)
+        ev = evaluate(L, (B, C, Hf, Wf, H, W)) if evaluate is not None else None
+        if ev is not None and upsampled:
+            t_ptr, t_bs, t_cs, pt_ptr, pidx_ptr, words_ptr, idx_ptr = ev
+            call("rhseg_head_level_fwd_eval", ptr(f), ptr(eff_w), ptr(eff_b),
+                 ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
+                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum),
+                 t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, words_ptr, idx_ptr, st)
+        else:
+            call("rhseg_head_level_fwd", ptr(f), ptr(eff_w), ptr(eff_b),
+                 ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
+                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum), 0, st)
+            if ev is not None:
+                t_ptr, t_bs, t_cs, pt_ptr, pidx_ptr, words_ptr, idx_ptr = ev
+                call("rhseg_level_eval", ptr(z), t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, ptr(tables[L]),
+                     B, K, n_pix, 1 if L > 0 else 0, words_ptr, idx_ptr, st)
         probs.append(p); logits.append(z); psums.append(psum); eff_ws.append(eff_w); gbs.append(gb)
     return dict(feats=feats, head_w=head_w, head_b=head_b, film_w=film_w, film_b=film_b, probs=probs, logits=logits,
                 psums=psums, eff_ws=eff_ws, gbs=gbs, dims=(B, C, Hf, Wf, H, W), upsampled=upsampled)
