@@ -263,11 +263,13 @@ int rhseg_step_finalize(const void* eval_words, const float* weights_all, int B,
  *   map (uint8 [B,n_pix]) as written by this function for that level; both NULL at level 0.
  *   out_words (8-byte words, zeroed here):
  *     [B*K*RHSEG_NSTAT fp64 statistics][RHSEG_MAX_K fp64 consistency sums][nc*nc int64 confusion]
- *   idx_out: uint8 [B,n_pix] prediction index map (NULL when no deeper level needs it).      */
+ *   idx_out: uint8 [B,n_pix] prediction index map (NULL when no deeper level needs it).
+ *   ctas_per_sm: 2 (default, 0 means 2) fills the GPU; 1 halves the footprint so that a kernel
+ *   launched on another stream (the next level's forward) can be co-resident.               */
 int rhseg_level_eval(const float* logits, const float* targets, long t_bstride, long t_cstride,
                      const float* parent_targets, long pt_bstride, long pt_cstride,
                      const unsigned char* prev_idx, const int32_t* table, int B, int K, int n_pix,
-                     int child, void* out_words, unsigned char* idx_out, void* stream);
+                     int child, void* out_words, unsigned char* idx_out, int ctas_per_sm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -374,7 +374,7 @@ static int tune_env(const char* name) {
   return v ? atoi(v) : 0;
 }
 using BwdCfgV4 = PipeCfg<8, 8, 3>;  // 8 consumer warps x float4 -> T = 1024 px, 4 KB row copies, 33 KB stages
-using BwdCfgS1 = PipeCfg<8, 8, 3>;  // scalar rows: T = 256*J px
+using BwdCfgS1 = PipeCfg<8, 16, 2>;  // scalar rows: T = 256*J px, 66 KB stages (dz reused over 16 channels)
 
 // ------------------------------------------------------------------------------------
 // parameter gradients (tiny): one thread per feature channel
@@ -530,15 +530,15 @@ extern "C" int rhseg_head_conv_bwd(const float* feats, const float* dz, const fl
       if constexpr (KK == 4) {
         const int t = tune_env("RHSEG_TUNE_BWD_V4");
         if (t == 1) return launch_conv_bwd<KK, 4, 1, PipeCfg<4, 8, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
-        if (t == 2) return launch_conv_bwd<KK, 4, 1, PipeCfg<4, 16, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
-        if (t == 3) return launch_conv_bwd<KK, 4, 1, PipeCfg<8, 8, 4>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+        if (t == 2) return launch_conv_bwd<KK, 4, 1, PipeCfg<8, 16, 2>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+        if (t == 3) return launch_conv_bwd<KK, 4, 1, PipeCfg<8, 16, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
       }
       return launch_conv_bwd<KK, 4, 1, BwdCfgV4>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
     }
     if constexpr (KK == 4) {
       const int t = tune_env("RHSEG_TUNE_BWD_S1");
-      if (t == 1) return launch_conv_bwd<KK, 1, 2, PipeCfg<8, 8, 4>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
-      if (t == 2) return launch_conv_bwd<KK, 1, 4, PipeCfg<4, 8, 4>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+      if (t == 1) return launch_conv_bwd<KK, 1, 4, PipeCfg<8, 16, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+      if (t == 2) return launch_conv_bwd<KK, 1, 4, PipeCfg<8, 24, 2>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
       if (t == 3) return launch_conv_bwd<KK, 1, 4, PipeCfg<8, 16, 2>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
     }
     return launch_conv_bwd<KK, 1, (KK <= 4 ? 4 : 2), BwdCfgS1>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);

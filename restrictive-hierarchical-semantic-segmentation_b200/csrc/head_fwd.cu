@@ -643,8 +643,8 @@ static int fwd_fullres(const float* feats, const float* eff_w, const float* eff_
     if constexpr (K == 4) {
       const int t = tune_env("RHSEG_TUNE_FWD_V4");
       if (t == 1) return launch_fwd<K, 4, 1, MODE, PipeCfg<4, 8, 4>>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st);
-      if (t == 2) return launch_fwd<K, 4, 1, MODE, PipeCfg<4, 16, 3>>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st);
-      if (t == 3) return launch_fwd<K, 4, 1, MODE, PipeCfg<8, 8, 4>>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st);
+      if (t == 2) return launch_fwd<K, 4, 1, MODE, PipeCfg<8, 16, 2>>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st);
+      if (t == 3) return launch_fwd<K, 4, 1, MODE, PipeCfg<8, 16, 3>>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st);
     }
     return launch_fwd<K, 4, 1, MODE, FwdCfgV4>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st);
   }

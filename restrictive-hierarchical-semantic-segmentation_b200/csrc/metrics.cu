@@ -268,7 +268,7 @@ extern "C" int rhseg_metric_ratios(const int64_t* conf, int nc, float* out5, voi
 extern "C" int rhseg_level_eval(const float* logits, const float* targets, long t_bstride, long t_cstride,
                                 const float* parent_targets, long pt_bstride, long pt_cstride,
                                 const unsigned char* prev_idx, const int32_t* table, int B, int K, int n_pix,
-                                int child, void* out_words, unsigned char* idx_out, void* stream) {
+                                int child, void* out_words, unsigned char* idx_out, int ctas_per_sm, void* stream) {
   if (!logits || !targets || !out_words || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   if (child && !table) return RHSEG_ERR_ARG;
@@ -281,7 +281,8 @@ extern "C" int rhseg_level_eval(const float* logits, const float* targets, long 
   unsigned long long* conf = reinterpret_cast<unsigned long long*>(cons + RHSEG_MAX_K);
   const long N = n_pix;
   constexpr int THREADS = 256, ITER = 1;
-  const int slots = std::max(1, device_sm_count() * 2 / B);  // CTAs per sample for one resident wave (2 CTAs/SM)
+  // CTAs per sample for one resident wave; ctas_per_sm = 1 leaves room for a concurrently running kernel
+  const int slots = std::max(1, device_sm_count() * (ctas_per_sm == 1 ? 1 : 2) / B);
   bool v4 = (N % 4 == 0) && aligned16(logits) && aligned16(targets) && t_bstride % 4 == 0 && t_cstride % 4 == 0 &&
             (reinterpret_cast<uintptr_t>(prev_idx) % 4 == 0) && (reinterpret_cast<uintptr_t>(idx_out) % 4 == 0);
   if (parent_targets) v4 = v4 && aligned16(parent_targets) && pt_bstride % 4 == 0 && pt_cstride % 4 == 0;

@@ -24,6 +24,17 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    """One auxiliary stream per device for kernels that are independent of the level chain."""
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
     """Runs the per-level forward kernels.  `tensors` = feats[n] + head_w[n] + head_b[n] + film_w[n-1] +
     film_b[n-1].  Returns a dict with the inputs (contiguous fp32) and probs / logits / psums / eff_w /
@@ -49,6 +60,7 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
     # every level's fp64 pool sums live in one buffer zeroed by a single fill
     psum_all = torch.zeros((sum(tree.head_channels) * B,), dtype=torch.float64, device=dev)
     psum_off = 0
+    used_side = False
     for L in range(n):
         K = tree.head_channels[L]
         K_prev = tree.head_channels[L - 1] if L > 0 else 0
@@ -71,8 +83,15 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
         psum_off += B * K
         z_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev) if upsampled else None
         ev = evaluate(L, (B, C, Hf, Wf, H, W)) if evaluate is not None else None
-        if ev is not None and upsampled:
+        # The evaluation of level L only needs its logits (and the previous level's index map): for all
+        # but the last level it runs on a side stream, overlapping the (memory-bound) forward of the next
+        # level; the last level's evaluation is fused into its hi-res forward kernel when there is one.
+        overlap = ev is not None and L < n - 1
+        if ev is not None and upsampled and not overlap:
             t_ptr, t_bs, t_cs, pt_ptr, pidx_ptr, words_ptr, idx_ptr = ev
+            if used_side:  # the previous level's index map is produced on the side stream
+                torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
+                used_side = False
             call("rhseg_head_level_fwd_eval", ptr(f), ptr(eff_w), ptr(eff_b),
                  ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
                  B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum),
@@ -83,9 +102,22 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
                  B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum), 0, st)
             if ev is not None:
                 t_ptr, t_bs, t_cs, pt_ptr, pidx_ptr, words_ptr, idx_ptr = ev
-                call("rhseg_level_eval", ptr(z), t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, ptr(tables[L]),
-                     B, K, n_pix, 1 if L > 0 else 0, words_ptr, idx_ptr, st)
+                if overlap:
+                    main = torch.cuda.current_stream(dev)
+                    side = _side_stream(dev)
+                    side.wait_stream(main)  # logits of this level (and everything before) are ready
+                    call("rhseg_level_eval", ptr(z), t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, ptr(tables[L]),
+                         B, K, n_pix, 1 if L > 0 else 0, words_ptr, idx_ptr, 2, side.cuda_stream)
+                    used_side = True
+                else:
+                    if used_side:  # the previous level's index map is produced on the side stream
+                        torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
+                        used_side = False
+                    call("rhseg_level_eval", ptr(z), t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, ptr(tables[L]),
+                         B, K, n_pix, 1 if L > 0 else 0, words_ptr, idx_ptr, 2, st)
         probs.append(p); logits.append(z); psums.append(psum); eff_ws.append(eff_w); gbs.append(gb)
+    if used_side:
+        torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
     return dict(feats=feats, head_w=head_w, head_b=head_b, film_w=film_w, film_b=film_b, probs=probs, logits=logits,
                 psums=psums, eff_ws=eff_ws, gbs=gbs, dims=(B, C, Hf, Wf, H, W), upsampled=upsampled)
 

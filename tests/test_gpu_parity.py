@@ -291,3 +291,29 @@ def test_dropin_unet_module_matches_oracle():
         close(logits[L], z_ref[L], rtol=2e-5, what=f"logits{L}")
         close(probs[L], p_ref[L], rtol=2e-5, what=f"probs{L}")
     assert m.levels == levels and m.parent_of == parent_of
+
+
+def test_flat_seven_class_losses_and_metrics_match_reference():
+    """BASELINE.json configs[3]: flat 7-class weighted Dice+CE (reference-generated fixture) and the
+    confusion-matrix metrics of its argmax prediction (oracle's restated torchmetrics slice)."""
+    import os
+    import numpy as np
+    from helpers import GOLDEN
+    from rhseg_b200 import metric_ops
+    from rhseg_b200.Metrics import losses, performance_metrics as pm
+    z = np.load(os.path.join(GOLDEN, "flat7.npz"))
+    logits = torch.from_numpy(z["logits"]).to(DEV).requires_grad_(True)
+    t = torch.from_numpy(z["target"]).float().to(DEV)
+    w = [float(v) for v in z["weights"]]
+    ce = losses.CrossEntropyLoss()(logits, t, class_weight=w, logits_input=True)
+    di = losses.SoftDiceLoss(num_classes=7)(logits, t, class_weight=w, logits_input=True)
+    assert abs(ce.item() - float(z["ce"])) <= 1e-5 and abs(di.item() - float(z["dice"])) <= 1e-5
+    (ce + di).backward()
+    close(logits.grad, z["dlogits"], what="flat dlogits")
+    # train.py:206-216 for model_type 0: one-hot of argmax(softmax), no -1 in flat targets
+    onehot, eval_t = metric_ops.predict_onehot(logits.detach(), t)
+    ref_oh, ref_et = O.predict_onehot_masked([logits.detach().cpu()], [t.cpu()])
+    assert torch.equal(onehot.cpu(), ref_oh[0])
+    want = O.level_metrics(ref_oh[0], ref_et[0], 7, False)
+    for key, mod in (("iou", pm.Jaccardindex()), ("dice", pm.DiceScore()), ("recall", pm.Recall())):
+        assert torch.equal(mod(onehot, eval_t, DEV, 7, False).cpu(), want[key])
