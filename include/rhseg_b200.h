@@ -133,9 +133,10 @@ int rhseg_head_act_bwd(const float* logits, const float* prev_probs, const int32
                        float* dz_out, float* dp_prev, void* stream);
 
 /* Adjoint of the bilinear align_corners=True upsample: dz_hi [B,K,H,W] -> dz_lo [B,K,Hf,Wf]
- * (deterministic, shared-memory tiled and separable).                                     */
+ * (deterministic, separable).  tmp: optional workspace [B,K,H,Wf] fp32; with it (and W % 4 == 0)
+ * the halo-free row kernel is used, otherwise the shared-memory tiled kernel.              */
 int rhseg_upsample_adjoint(const float* dz_hi, int B, int K, int Hf, int Wf, int H, int W,
-                           float* dz_lo, void* stream);
+                           float* dz_lo, float* tmp, void* stream);
 
 /* Fused hi-res backward for upsampled heads (HRNet): forms per hi-res pixel
  *   dz_hi = d(g_ce*CE + g_dice*Dice)/dz  (closed form from logits, targets, coef of
@@ -147,7 +148,7 @@ int rhseg_head_dz_lowres_fused(const float* logits, const float* targets, long t
                                const float* prev_probs, const int32_t* table, const double* g_uniform,
                                double inv_npix, const float* dp_pix, uint32_t pix_mask,
                                int B, int K, int K_prev, int Hf, int Wf, int H, int W, int act_mode,
-                               float* dz_lo, float* dp_prev, void* stream);
+                               float* dz_lo, float* dp_prev, float* tmp, void* stream);
 
 /* 1x1 conv backward at feature resolution: dfeats[b,c,n] = sum_k eff_w[b,k,c] dz[b,k,n];
  * S[b,k,c] = sum_n dz[b,k,n] feats[b,c,n]; s[b,k] = sum_n dz[b,k,n]  (fp64, accumulated with

@@ -183,6 +183,162 @@ upsample_adjoint_tiled_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, i
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Halo-free separable adjoint for row-aligned inputs (the HRNet case): pass 1 handles ROWS full
+// hi-res rows per CTA (every hi-res pixel's gradient is formed exactly once), reduces them along x
+// into tmpx [B,K,H,Wf]; pass 2 reduces tmpx along y.  Used when W % 4 == 0 and the taps per low-res
+// index fit XR_MAXW; the tiled kernel above is the generic fallback.
+// ------------------------------------------------------------------------------------
+constexpr int XR_ROWS = 4, XR_THREADS = 256, XR_MAXW = 12;
+
+template <int K, int SRC, int MODE>
+__global__ void __launch_bounds__(XR_THREADS)
+dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, int H, int W, float sx,
+                       float* __restrict__ tmpx) {
+  extern __shared__ __align__(16) float sm[];
+  const int Wp = W + 4;
+  float* dzs = sm;                                   // [K][XR_ROWS][Wp]
+  float* wtab = sm + (size_t)K * XR_ROWS * Wp;       // [Wf][XR_MAXW]
+  int* wstart = reinterpret_cast<int*>(wtab + (size_t)Wf * XR_MAXW);  // [Wf]
+  int* wcnt = wstart + Wf;                           // [Wf]
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int y0 = blockIdx.x * XR_ROWS;
+  const int rows = min(XR_ROWS, H - y0);
+  const long N = (long)H * W;
+
+  for (int j = tid; j < Wf; j += XR_THREADS) {
+    int lo, hi;
+    lerp_support(j, sx, W, lo, hi);
+    int first = -1, cnt = 0;
+    for (int x = lo; x <= hi; ++x) {
+      const float w = lerp_weight(x, sx, Wf, j);
+      if (w != 0.f || first >= 0) {
+        if (first < 0) first = x;
+        if (cnt < XR_MAXW) wtab[j * XR_MAXW + cnt] = w;
+        ++cnt;
+      }
+    }
+    wstart[j] = first < 0 ? lo : first;
+    wcnt[j] = cnt < XR_MAXW ? cnt : XR_MAXW;
+  }
+
+  // ---- phase 1: gradient of ROWS full rows -> shared memory (4 pixels per thread and step) ----
+  const int vec_per_row = W / 4;
+  if constexpr (SRC == 0) {
+    for (int e = tid; e < rows * vec_per_row; e += XR_THREADS) {
+      const int r = e / vec_per_row, xv = (e - r * vec_per_row) * 4;
+      const size_t px = (size_t)(y0 + r) * W + xv;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(dz_hi + ((size_t)b * K + k) * N + px);
+        *reinterpret_cast<float4*>(dzs + ((size_t)k * XR_ROWS + r) * Wp + xv) = v;
+      }
+    }
+  } else {
+    const LevelInfo li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? fa.table : nullptr);
+    const float gce = fa.g_ce ? __ldg(fa.g_ce) : 0.f, gdi = fa.g_dice ? __ldg(fa.g_dice) : 0.f;
+    float A[K], Bc[K], Cc[K], gu[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float* cf = fa.coef + ((size_t)b * K + k) * 3;
+      A[k] = gce * __ldg(cf);
+      Bc[k] = gdi * __ldg(cf + 1);
+      Cc[k] = gdi * __ldg(cf + 2);
+      gu[k] = fa.g_uniform ? (float)fa.g_uniform[b * K + k] * fa.inv_npix : 0.f;
+    }
+    const bool has_act = MODE != RHSEG_ACT_ZEROS && (fa.g_uniform != nullptr || (fa.dp_pix != nullptr && fa.pix_mask != 0));
+    for (int e = tid; e < rows * vec_per_row; e += XR_THREADS) {
+      const int r = e / vec_per_row, xv = (e - r * vec_per_row) * 4;
+      const size_t px = (size_t)(y0 + r) * W + xv;
+      float z[K][4], t[K][4], ex[K][4], pp[K][4], o[K][4], dpar[K][4];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const Vec<4> zv = ld_stream<4>(fa.logits + ((size_t)b * K + k) * N + px);
+        const Vec<4> tv = ld_cached<4>(fa.targets + (size_t)b * fa.t_bstride + (size_t)k * fa.t_cstride + px);
+        Vec<4> ev;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) ev.v[v] = 0.f;
+        if (has_act && fa.dp_pix && ((fa.pix_mask >> k) & 1u)) ev = ld_stream<4>(fa.dp_pix + ((size_t)b * K + k) * N + px);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { z[k][v] = zv.v[v]; t[k][v] = tv.v[v]; ex[k][v] = ev.v[v]; pp[k][v] = 0.f; }
+      }
+      if constexpr (MODE == RHSEG_ACT_GROUPED) {
+        if (has_act) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            if ((li.start_mask >> k) & 1) {
+              const Vec<4> pv = ld_stream<4>(fa.prev_probs + ((size_t)b * fa.K_prev + li.parent[k]) * N + px);
+#pragma unroll
+              for (int v = 0; v < 4; ++v) pp[k][v] = pv.v[v];
+            } else {
+#pragma unroll
+              for (int v = 0; v < 4; ++v) pp[k][v] = pp[k > 0 ? k - 1 : 0][v];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float zz[K], tt[K], dz[K], dP[K], ppv[K], dpv[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { zz[k] = z[k][v]; tt[k] = t[k][v]; dP[k] = gu[k] + ex[k][v]; ppv[k] = pp[k][v]; dpv[k] = 0.f; }
+        loss_dz_pixel<K, true>(zz, tt, A, Bc, Cc, dz);
+        if (has_act) act_dz_pixel<K, MODE>(zz, dP, ppv, li.start_mask, dz, dpv);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { o[k][v] = dz[k]; dpar[k][v] = dpv[k]; }
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        *reinterpret_cast<float4*>(dzs + ((size_t)k * XR_ROWS + r) * Wp + xv) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+      if constexpr (MODE == RHSEG_ACT_GROUPED) {
+        if (has_act && fa.dp_prev) {
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            if ((li.start_mask >> k) & 1) {
+              float* dst = fa.dp_prev + ((size_t)b * fa.K_prev + li.parent[k]) * N + px;
+              float4 cur = *reinterpret_cast<const float4*>(dst);
+              cur.x += dpar[k][0]; cur.y += dpar[k][1]; cur.z += dpar[k][2]; cur.w += dpar[k][3];
+              *reinterpret_cast<float4*>(dst) = cur;
+            }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: reduce along x: tmpx[b][k][y][j] = sum_x wx(x, j) dz[k][y][x] ----
+  for (int e = tid; e < K * rows * Wf; e += XR_THREADS) {
+    const int j = e % Wf;
+    const int kr = e / Wf;
+    const int r = kr % rows, k = kr / rows;
+    const float* row = dzs + ((size_t)k * XR_ROWS + r) * Wp + wstart[j];
+    const float* wt = wtab + j * XR_MAXW;
+    const int n = wcnt[j];
+    float acc = 0.f;
+    for (int q = 0; q < n; ++q) acc = fmaf(wt[q], row[q], acc);
+    tmpx[(((size_t)b * K + k) * H + y0 + r) * Wf + j] = acc;
+  }
+}
+
+// pass 2: dz_lo[b][k][i][j] = sum_y wy(y, i) tmpx[b][k][y][j]
+__global__ void __launch_bounds__(256)
+yreduce_kernel(const float* __restrict__ tmpx, int Hf, int Wf, int H, float sy, long total, float* __restrict__ dz_lo) {
+  const long idx = (long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % Wf);
+  const int i = (int)((idx / Wf) % Hf);
+  const long bk = idx / ((long)Wf * Hf);
+  int lo, hi;
+  lerp_support(i, sy, H, lo, hi);
+  const float* col = tmpx + (size_t)bk * H * Wf + j;
+  float acc = 0.f;
+  for (int y = lo; y <= hi; ++y) {
+    const float w = lerp_weight(y, sy, Hf, i);
+    if (w != 0.f) acc = fmaf(w, __ldg(col + (size_t)y * Wf), acc);
+  }
+  dz_lo[idx] = acc;
+}
+
 // Full-resolution donors (UNet): the same fused per-pixel gradient, written out once as dz.
 template <int K, int VEC, int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
@@ -270,9 +426,28 @@ static int region_extent(int t, float scale, int out_size) {
 
 template <int K, int SRC, int MODE>
 static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int Hf, int Wf, int H, int W, float* dz_lo,
-                          cudaStream_t st) {
+                          float* tmpx, cudaStream_t st) {
   const float sy = H > 1 ? (float)(Hf - 1) / (float)(H - 1) : 0.f;
   const float sx = W > 1 ? (float)(Wf - 1) / (float)(W - 1) : 0.f;
+  {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    bool rows_ok = tmpx != nullptr && W % 4 == 0 && sx > 0.f && 2.0f / sx + 3.0f <= (float)XR_MAXW;
+    if (SRC == 0) rows_ok = rows_ok && al(dz_hi);
+    else rows_ok = rows_ok && al(fa.logits) && al(fa.targets) && fa.t_bstride % 4 == 0 && fa.t_cstride % 4 == 0 &&
+                   al(fa.prev_probs) && al(fa.dp_pix) && al(fa.dp_prev);
+    const size_t smem = ((size_t)K * XR_ROWS * (W + 4) + (size_t)Wf * XR_MAXW + 2 * (size_t)Wf) * sizeof(float);
+    if (rows_ok && smem <= 160 * 1024) {
+      auto kern = dz_rows_xreduce_kernel<K, SRC, MODE>;
+      if (smem > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid((H + XR_ROWS - 1) / XR_ROWS, B);
+      kern<<<grid, XR_THREADS, smem, st>>>(dz_hi, fa, Wf, H, W, sx, tmpx);
+      RHSEG_LAUNCH_CHECK();
+      const long total = (long)B * K * Hf * Wf;
+      yreduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tmpx, Hf, Wf, H, sy, total, dz_lo);
+      RHSEG_LAUNCH_CHECK();
+      return RHSEG_OK;
+    }
+  }
   const int ry_max = region_extent(ADJ_TH, sy, H), rx_max = region_extent(ADJ_TW, sx, W) | 1;  // odd pitch: fewer bank conflicts
   const size_t smem = ((size_t)K * ry_max * rx_max + (size_t)K * ry_max * ADJ_TW) * sizeof(float);
   if (smem > 200 * 1024) return RHSEG_ERR_UNSUPPORTED;  // upsampling factor too large for the tiled kernel
@@ -292,11 +467,11 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
 using namespace rhseg;
 
 extern "C" int rhseg_upsample_adjoint(const float* dz_hi, int B, int K, int Hf, int Wf, int H, int W, float* dz_lo,
-                                      void* stream) {
+                                      float* tmp, void* stream) {
   if (!dz_hi || !dz_lo || B <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   FusedDzArgs fa{};
-  RHSEG_DISPATCH_K(K, return (launch_adjoint<KK, 0, 0>(dz_hi, fa, B, Hf, Wf, H, W, dz_lo, (cudaStream_t)stream)));
+  RHSEG_DISPATCH_K(K, return (launch_adjoint<KK, 0, 0>(dz_hi, fa, B, Hf, Wf, H, W, dz_lo, tmp, (cudaStream_t)stream)));
   return RHSEG_OK;
 }
 
@@ -305,7 +480,7 @@ extern "C" int rhseg_head_dz_lowres_fused(const float* logits, const float* targ
                                           const float* prev_probs, const int32_t* table, const double* g_uniform,
                                           double inv_npix, const float* dp_pix, uint32_t pix_mask, int B, int K,
                                           int K_prev, int Hf, int Wf, int H, int W, int act_mode, float* dz_lo,
-                                          float* dp_prev, void* stream) {
+                                          float* dp_prev, float* tmp, void* stream) {
   if (!logits || !targets || !coef || !dz_lo || B <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   if (act_mode == RHSEG_ACT_GROUPED && (!prev_probs || !table)) return RHSEG_ERR_ARG;
@@ -313,9 +488,9 @@ extern "C" int rhseg_head_dz_lowres_fused(const float* logits, const float* targ
                  (float)inv_npix, dp_pix, pix_mask, dp_prev, K_prev};
   cudaStream_t st = (cudaStream_t)stream;
   RHSEG_DISPATCH_K(K, {
-    if (act_mode == RHSEG_ACT_SIGMOID) return launch_adjoint<KK, 1, RHSEG_ACT_SIGMOID>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, st);
-    if (act_mode == RHSEG_ACT_GROUPED) return launch_adjoint<KK, 1, RHSEG_ACT_GROUPED>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, st);
-    return launch_adjoint<KK, 1, RHSEG_ACT_ZEROS>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, st);
+    if (act_mode == RHSEG_ACT_SIGMOID) return launch_adjoint<KK, 1, RHSEG_ACT_SIGMOID>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, st);
+    if (act_mode == RHSEG_ACT_GROUPED) return launch_adjoint<KK, 1, RHSEG_ACT_GROUPED>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, st);
+    return launch_adjoint<KK, 1, RHSEG_ACT_ZEROS>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, st);
   });
   return RHSEG_OK;
 }

@@ -161,9 +161,10 @@ class _FusedStepFn(torch.autograd.Function):
             c_ptr = coef_all.data_ptr() + coef_offs[L] * 4
             if ctx.upsampled:
                 dz = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev)
+                tmpx = torch.empty((B, K, H, Wf), dtype=torch.float32, device=dev)
                 call("rhseg_head_dz_lowres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, ptr(g), ptr(g),
                      ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]), ptr(g_uniform), 1.0 / n_pix, ptr(dp_pix),
-                     pix_mask, B, K, K_prev, Hf, Wf, H, W, mode, ptr(dz), ptr(dp_prev), st)
+                     pix_mask, B, K, K_prev, Hf, Wf, H, W, mode, ptr(dz), ptr(dp_prev), ptr(tmpx), st)
             else:
                 dz = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
                 call("rhseg_head_dz_fullres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, ptr(g), ptr(g),

@@ -226,7 +226,8 @@ class _HierHeadFn(torch.autograd.Function):
                 continue  # nothing reaches this level's logits: no gradient for its features / parameters
             if ctx.upsampled:
                 dz_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev)
-                call("rhseg_upsample_adjoint", ptr(dz), B, K, Hf, Wf, H, W, ptr(dz_lo), st)
+                tmpx = torch.empty((B, K, H, Wf), dtype=torch.float32, device=dev)
+                call("rhseg_upsample_adjoint", ptr(dz), B, K, Hf, Wf, H, W, ptr(dz_lo), ptr(tmpx), st)
                 dz = dz_lo
             S, s = sums[L]
             d_feats[L], d_hw[L], d_hb[L], fw_g, fb_g, g_prev = level_weight_backward(
