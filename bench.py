@@ -405,7 +405,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches_per_step": launches_per_step,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference(wl, steps=2, warmup=1, sample_b=1)
+        line["cpu_baseline"] = cpu_reference(wl, steps=20, warmup=2, sample_b=1)  # ~10 s of host work
     return line
 
 
