@@ -34,6 +34,8 @@ extern "C" {
 #define RHSEG_TABLE_INTS (4 + 5 * RHSEG_MAX_K)
 #define RHSEG_NSTAT 5            /* per (sample, class) loss statistics, see loss_stats   */
 #define RHSEG_MAX_LEVELS 8       /* tree depth rhseg_step_finalize handles in one launch  */
+#define RHSEG_STITCH_MAX_LEAVES 16 /* leaf channels of a flat model rhseg_stitch_levels reads */
+#define RHSEG_STITCH_MAX_OUT 32    /* tree nodes (output channels) it writes                 */
 
 enum {
   RHSEG_OK = 0,
@@ -271,6 +273,13 @@ int rhseg_level_eval(const float* logits, const float* targets, long t_bstride, 
                      const float* parent_targets, long pt_bstride, long pt_cstride,
                      const unsigned char* prev_idx, const int32_t* table, int B, int K, int n_pix,
                      int child, void* out_words, unsigned char* idx_out, int ctas_per_sm, void* stream);
+
+/* Flat -> hierarchy stitching (predictEval.py:85-185, :381-388): `leaves` [B,n_leaves,n_pix] are the
+ * flat model's leaf channels (predictions or targets); `out` [B,n_out,n_pix] gets one channel per tree
+ * node in level order: masks[o] bit 31 set = copy leaf channel (the single low bit set), clear = union
+ * (any > 0 -> 1.0) of the leaf channels whose low bits are set.  masks is a HOST array.          */
+int rhseg_stitch_levels(const float* leaves, int B, int n_leaves, int n_pix, const uint32_t* masks,
+                        int n_out, float* out, void* stream);
 
 #ifdef __cplusplus
 }

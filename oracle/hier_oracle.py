@@ -317,6 +317,49 @@ def all_level_metrics(outputs, targets):
 
 
 # --------------------------------------------------------------------------
+# (f3) flat -> hierarchy stitching
+# --------------------------------------------------------------------------
+def stitch_flat_to_levels(flat, tree: dict):
+    """predictEval.py:85-185 (get_parent_masks + combine_levels) as predict() calls them (:381-388):
+    flat leaf channels (breadth-first leaf order) -> per-level tensors; a parent is the union
+    (any > 0) of its descendant leaves."""
+    from collections import deque
+    children = {}
+    stack = [tree]
+    while stack:
+        t = stack.pop()
+        for k, v in t.items():
+            children[k] = list(v.keys()) if isinstance(v, dict) and len(v) > 0 else []
+            if children[k]:
+                stack.append(v)
+    q, bfs, levels = deque((n, s, 0) for n, s in tree.items()), [], []
+    while q:
+        name, sub, d = q.popleft()
+        bfs.append(name)
+        if len(levels) <= d:
+            levels.append([])
+        levels[d].append(name)
+        if isinstance(sub, dict) and len(sub) > 0:
+            q.extend((cn, cs, d + 1) for cn, cs in sub.items())
+    leaf_idx = {n: i for i, n in enumerate(n for n in bfs if not children[n])}
+
+    def leaves_under(n):
+        return [n] if not children[n] else [l for c in children[n] for l in leaves_under(c)]
+
+    out = []
+    for names in levels:
+        chans = []
+        for n in names:
+            if not children[n]:
+                chans.append(flat[:, leaf_idx[n]:leaf_idx[n] + 1])
+            else:
+                idx = sorted(set(leaf_idx[l] for l in leaves_under(n)))
+                chans.append((flat[:, idx] > 0).any(dim=1, keepdim=True).to(flat.dtype))
+        out.append(torch.cat(chans, dim=1))
+    return out
+
+
+# --------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md 8(d)) — shared by tests, smoke and bench
 # --------------------------------------------------------------------------
 def synth_targets(levels, groups, B, H, W, gen: torch.Generator, blobs: bool = False, device="cpu"):

@@ -189,6 +189,52 @@ level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ ta
   ev.template finish<THREADS / 32>(&red[0][0], hist, stats, cons, conf, table, b);
 }
 
+// ------------------------------------------------------------------------------------
+// Flat -> hierarchy stitching (predictEval.py:85-185, :381-388): the flat model predicts the
+// leaves only; every node of the tree becomes one output channel: a leaf copies its flat channel,
+// a parent is the union (any > 0) of its descendant leaves.  Table driven: one uint32 leaf mask
+// per output channel, bit 31 set = "copy" (leaf), clear = "union" (parent).
+// ------------------------------------------------------------------------------------
+struct StitchTable {
+  int n_out;
+  uint32_t mask[RHSEG_STITCH_MAX_OUT];
+};
+
+template <int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+stitch_kernel(const float* __restrict__ leaves, int n_leaves, long N, StitchTable tab, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const long px = ((long)blockIdx.x * THREADS + threadIdx.x) * VEC;
+  if (px >= N) return;
+  float x[RHSEG_STITCH_MAX_LEAVES][VEC];
+#pragma unroll
+  for (int l = 0; l < RHSEG_STITCH_MAX_LEAVES; ++l) {
+    if (l < n_leaves) {
+      const Vec<VEC> v = ld_stream<VEC>(leaves + ((size_t)b * n_leaves + l) * N + px);
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) x[l][q] = v.v[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) x[l][q] = 0.f;
+    }
+  }
+  for (int o = 0; o < tab.n_out; ++o) {
+    const uint32_t m = tab.mask[o];
+    const bool copy = (m >> 31) != 0u;
+    Vec<VEC> r;
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      float cp = 0.f;
+      bool any = false;
+#pragma unroll
+      for (int l = 0; l < RHSEG_STITCH_MAX_LEAVES; ++l)
+        if ((m >> l) & 1u) { cp = x[l][q]; any |= x[l][q] > 0.f; }
+      r.v[q] = copy ? cp : (any ? 1.0f : 0.0f);
+    }
+    st_stream<VEC>(out + ((size_t)b * tab.n_out + o) * N + px, r);
+  }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int MODE>
@@ -297,6 +343,30 @@ extern "C" int rhseg_level_eval(const float* logits, const float* targets, long 
           pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     }
   });
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+extern "C" int rhseg_stitch_levels(const float* leaves, int B, int n_leaves, int n_pix, const uint32_t* masks,
+                                   int n_out, float* out, void* stream) {
+  if (!leaves || !masks || !out || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
+  if (n_leaves < 1 || n_leaves > RHSEG_STITCH_MAX_LEAVES || n_out < 1 || n_out > RHSEG_STITCH_MAX_OUT) return RHSEG_ERR_UNSUPPORTED;
+  StitchTable tab{};
+  tab.n_out = n_out;
+  for (int o = 0; o < n_out; ++o) {
+    if ((masks[o] & 0x7fffffffu) >> n_leaves) return RHSEG_ERR_TREE;  // references a leaf that does not exist
+    tab.mask[o] = masks[o];
+  }
+  const long N = n_pix;
+  constexpr int THREADS = 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N % 4 == 0 && aligned16(leaves) && aligned16(out)) {
+    dim3 grid((unsigned)((N / 4 + THREADS - 1) / THREADS), B);
+    stitch_kernel<4, THREADS><<<grid, THREADS, 0, st>>>(leaves, n_leaves, N, tab, out);
+  } else {
+    dim3 grid((unsigned)((N + THREADS - 1) / THREADS), B);
+    stitch_kernel<1, THREADS><<<grid, THREADS, 0, st>>>(leaves, n_leaves, N, tab, out);
+  }
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }

@@ -92,3 +92,25 @@ def level_ratios(probs, targets, child_classes: bool) -> torch.Tensor:
     if len(_MEMO) > _MEMO_MAX:
         del _MEMO[0]
     return res
+
+
+def stitch_flat_to_levels(flat, tree):
+    """Flat model output / target [B, n_leaves, H, W] (leaf channels in breadth-first order) -> list of
+    per-level tensors [B, K_L, H, W] with every parent filled as the union of its descendant leaves
+    (predictEval.get_parent_masks + combine_levels, predictEval.py:85-185)."""
+    import ctypes
+    native.require_cuda(flat)
+    x = flat if flat.dtype == torch.float32 else flat.float()
+    x = x if x.is_contiguous() else x.contiguous()
+    B, nl, H, W = x.shape
+    masks, counts = tree.stitch_masks()
+    if nl != len(tree.leaf_order()):
+        raise native.NativeError("flat tensor has %d channels, the tree has %d leaves" % (nl, len(tree.leaf_order())))
+    out = torch.empty((B, len(masks), H, W), dtype=torch.float32, device=x.device)
+    arr = (ctypes.c_uint32 * len(masks))(*masks)
+    call("rhseg_stitch_levels", ptr(x), B, nl, H * W, arr, len(masks), ptr(out), stream_of(x))
+    levels, s = [], 0
+    for k in counts:
+        levels.append(out[:, s:s + k])
+        s += k
+    return levels

@@ -98,6 +98,56 @@ class ClassTree:
     def group_count(self, L):
         return 0 if L == 0 else len(self.child_groups[L - 1])
 
+    # ---- flat -> hierarchy stitching tables (predictEval.py:36-83) ----
+    def bfs_names(self):
+        """Breadth-first node order (predictEval.bfs_order): the channel order of class_map.csv."""
+        from collections import deque
+        q, order = deque(self.hierarchy.items()), []
+        while q:
+            name, sub = q.popleft()
+            order.append(name)
+            if isinstance(sub, dict) and sub:
+                q.extend(sub.items())
+        return order
+
+    def bfs_levels(self):
+        """predictEval.levels_bfs: names per depth in breadth-first order."""
+        from collections import deque
+        q, out = deque((n, s, 0) for n, s in self.hierarchy.items()), []
+        while q:
+            name, sub, d = q.popleft()
+            if len(out) <= d:
+                out.append([])
+            out[d].append(name)
+            if isinstance(sub, dict) and sub:
+                q.extend((cn, cs, d + 1) for cn, cs in sub.items())
+        return out
+
+    def leaf_order(self):
+        """Flat-model channel order: leaves in breadth-first order (predictEval.py:381)."""
+        return [n for n in self.bfs_names() if not self.children_of.get(n)]
+
+    def stitch_masks(self):
+        """(masks, per-level channel counts) for rhseg_stitch_levels: one uint32 per node in bfs_levels order."""
+        leaf_idx = {n: i for i, n in enumerate(self.leaf_order())}
+
+        def leaves_under(n):
+            kids = self.children_of.get(n, [])
+            return [n] if not kids else [l for k in kids for l in leaves_under(k)]
+
+        masks, counts = [], []
+        for names in self.bfs_levels():
+            counts.append(len(names))
+            for n in names:
+                if not self.children_of.get(n):
+                    masks.append((1 << 31) | (1 << leaf_idx[n]))
+                else:
+                    m = 0
+                    for l in leaves_under(n):
+                        m |= 1 << leaf_idx[l]
+                    masks.append(m)
+        return masks, counts
+
 
 _TREE_CACHE = {}
 

@@ -108,3 +108,21 @@ def test_eval_mode_consistency_and_metrics_on_composed_probs():
         want = O.level_metrics(probs[L].cpu(), targets[L], chans[L], L != 0)
         for key, mod in (("iou", pm.Jaccardindex()), ("accuracy", pm.Accuracy()), ("precision", pm.Precision())):
             assert torch.equal(mod(probs[L], t, DEV, chans[L], L != 0).cpu(), want[key]), (L, key)
+
+
+@pytest.mark.parametrize("tree_dict", [TL, EXT, ADV], ids=["tl", "ext", "adv"])
+def test_flat_to_hierarchy_stitching(tree_dict):
+    """predictEval's flat -> hierarchy stitching as one table-driven kernel, bit-exact."""
+    import rhseg_b200
+    from rhseg_b200 import metric_ops
+    tree = rhseg_b200.ClassTree(tree_dict)
+    nl = len(tree.leaf_order())
+    g = torch.Generator().manual_seed(nl)
+    for shape in ((2, 9, 11), (3, 16, 24)):
+        lab = torch.randint(0, nl + 1, shape, generator=g)  # class nl = "no leaf predicted"
+        flat = torch.nn.functional.one_hot(lab, nl + 1).permute(0, 3, 1, 2).float()[:, :nl].contiguous()
+        want = O.stitch_flat_to_levels(flat, tree_dict)
+        got = metric_ops.stitch_flat_to_levels(flat.to(DEV), tree)
+        assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in want]
+        for a, b in zip(got, want):
+            assert torch.equal(a.cpu(), b)

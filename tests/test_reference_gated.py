@@ -86,3 +86,26 @@ print("ok")
     env = dict(os.environ)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=REF, env=env, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_oracle_stitching_matches_reference_predicteval():
+    """oracle.stitch_flat_to_levels == predictEval.get_parent_masks + combine_levels on both shipped trees."""
+    import importlib
+    ref_shim, _ = _ref()
+    for n in ("matplotlib.colors", "skimage.measure", "skimage.color", "scipy", "sklearn"):
+        ref_shim._stub(n)
+    pe = importlib.import_module("predictEval")
+    from oracle import hier_oracle as O
+    for fname in ("class_tree_tl.json", "class_tree_tl_extended.json"):
+        tree = json.load(open(os.path.join(REF, fname)))
+        names = [n for n in pe.bfs_order(tree) if not pe.children_map(tree).get(n)]
+        idx = {n: i for i, n in enumerate(names)}
+        g = torch.Generator().manual_seed(3)
+        lab = torch.randint(0, len(names), (2, 9, 11), generator=g)
+        flat = torch.nn.functional.one_hot(lab, len(names)).permute(0, 3, 1, 2).float()
+        tgt = torch.nn.functional.one_hot(torch.randint(0, len(names), (2, 9, 11), generator=g), len(names)).permute(0, 3, 1, 2).float()
+        par, par_t, _ = pe.get_parent_masks([flat], [tgt], tree, idx)
+        parent_order = [n for n in pe.bfs_order(tree) if pe.children_map(tree).get(n)]
+        want = pe.combine_levels([flat], par, tree, names, parent_order)
+        got = O.stitch_flat_to_levels(flat, tree)
+        assert len(want) == len(got) and all(torch.equal(a, b) for a, b in zip(want, got))
