@@ -32,6 +32,7 @@ extern "C" {
 #define RHSEG_MAX_K 16           /* channels per level the table format holds            */
 #define RHSEG_KERNEL_MAX_K 8     /* channels per level the fused kernels are built for    */
 #define RHSEG_TABLE_INTS (4 + 5 * RHSEG_MAX_K)
+#define RHSEG_EVAL_PREZEROED 1   /* rhseg_level_eval / rhseg_head_level_fwd_eval flag       */
 #define RHSEG_NSTAT 5            /* per (sample, class) loss statistics, see loss_stats   */
 #define RHSEG_MAX_LEVELS 8       /* tree depth rhseg_step_finalize handles in one launch  */
 #define RHSEG_STITCH_MAX_LEAVES 16 /* leaf channels of a flat model rhseg_stitch_levels reads */
@@ -103,6 +104,8 @@ int rhseg_head_level_fwd(const float* feats, const float* eff_w, const float* ef
                          int B, int C, int Hf, int Wf, int H, int W, int K, int K_prev, int act_mode,
                          float* z_lo, float* logits, float* probs, double* psum, int zero_psum,
                          void* stream);
+/* zero_psum bit 1 (value 2): z_lo was zeroed by the caller (one fill for all levels); without it the
+ * low-res pass zeroes z_lo itself whenever pixel tiles are split between CTAs.               */
 
 /* Level forward of an UPSAMPLED head (HRNet) fused with rhseg_level_eval: the hi-res pass that
  * interpolates and activates the logits also evaluates them against the ternary targets while
@@ -116,7 +119,7 @@ int rhseg_head_level_fwd_eval(const float* feats, const float* eff_w, const floa
                               const float* targets, long t_bstride, long t_cstride,
                               const float* parent_targets, long pt_bstride, long pt_cstride,
                               const unsigned char* prev_idx, void* out_words, unsigned char* idx_out,
-                              void* stream);
+                              int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (2') head, backward (what autograd does for the reference; closed forms in DESIGN.md).
@@ -267,12 +270,11 @@ int rhseg_step_finalize(const void* eval_words, const float* weights_all, int B,
  *   out_words (8-byte words, zeroed here):
  *     [B*K*RHSEG_NSTAT fp64 statistics][RHSEG_MAX_K fp64 consistency sums][nc*nc int64 confusion]
  *   idx_out: uint8 [B,n_pix] prediction index map (NULL when no deeper level needs it).
- *   ctas_per_sm: 2 (default, 0 means 2) fills the GPU; 1 halves the footprint so that a kernel
- *   launched on another stream (the next level's forward) can be co-resident.               */
+ *   flags: RHSEG_EVAL_PREZEROED = the caller already zeroed out_words (one fill for all levels). */
 int rhseg_level_eval(const float* logits, const float* targets, long t_bstride, long t_cstride,
                      const float* parent_targets, long pt_bstride, long pt_cstride,
                      const unsigned char* prev_idx, const int32_t* table, int B, int K, int n_pix,
-                     int child, void* out_words, unsigned char* idx_out, int ctas_per_sm, void* stream);
+                     int child, void* out_words, unsigned char* idx_out, int flags, void* stream);
 
 /* Flat -> hierarchy stitching (predictEval.py:85-185, :381-388): `leaves` [B,n_leaves,n_pix] are the
  * flat model's leaf channels (predictions or targets); `out` [B,n_out,n_pix] gets one channel per tree

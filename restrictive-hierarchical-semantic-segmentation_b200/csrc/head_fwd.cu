@@ -598,7 +598,7 @@ upsample_act_tiled_kernel(const float* __restrict__ z_lo, const float* __restric
 template <int K, int VEC, int J, int MODE, typename CFG>
 static int launch_fwd(const float* feats, const float* eff_w, const float* eff_b, const float* prev_probs,
                       const int32_t* table, int B, int C, int N, int K_prev, float* logits, float* probs,
-                      double* psum, cudaStream_t st) {
+                      double* psum, cudaStream_t st, bool out_prezeroed = false) {
   constexpr int KP = pad_k(K);
   constexpr int T = CFG::CONSUMERS * J * VEC;
   const size_t smem = 128 + ((size_t)CFG::NS * CFG::CH * (T + 4) + (size_t)C * KP + CFG::NCW * K) * sizeof(float);
@@ -614,7 +614,7 @@ static int launch_fwd(const float* feats, const float* eff_w, const float* eff_b
   long grid = (long)device_sm_count() * per_sm;
   grid = std::min<long>(grid, tiles_total);  // every CTA owns >= n_stages units: a split tile has <= 2 owners
   if (grid < 1) grid = 1;
-  if (MODE == MODE_CONV_ONLY && grid > 1)
+  if (MODE == MODE_CONV_ONLY && grid > 1 && !out_prezeroed)
     RHSEG_CUDA(cudaMemsetAsync(logits, 0, sizeof(float) * (size_t)B * K * N, st));
   const int a0 = (int)((reinterpret_cast<uintptr_t>(feats) >> 2) & 3);
   kern<<<(unsigned)grid, CFG::THREADS, smem, st>>>(feats, eff_w, eff_b, prev_probs, table, C, N, K_prev, n_tiles, n_stages,
@@ -727,7 +727,8 @@ static int level_fwd_impl(const float* feats, const float* eff_w, const float* e
   if (act_mode == RHSEG_ACT_GROUPED && (!prev_probs || !table || K_prev < 1)) return RHSEG_ERR_ARG;
   if (act_mode < 0 || act_mode > RHSEG_ACT_ZEROS) return RHSEG_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (zero_psum) RHSEG_CUDA(cudaMemsetAsync(psum, 0, sizeof(double) * B * K, st));
+  if (zero_psum & 1) RHSEG_CUDA(cudaMemsetAsync(psum, 0, sizeof(double) * B * K, st));
+  const bool zlo_zeroed = (zero_psum & 2) != 0;
   const bool up = (H != Hf) || (W != Wf);
   if (ea && !up) return RHSEG_ERR_UNSUPPORTED;
   const int Nf = Hf * Wf;
@@ -744,7 +745,7 @@ static int level_fwd_impl(const float* feats, const float* eff_w, const float* e
   RHSEG_DISPATCH_K(K, {
     int rc;
     if (rows_vec4(feats, Nf) && rows_vec4(z_lo, Nf)) {
-      rc = launch_fwd<KK, 4, 1, MODE_CONV_ONLY, FwdCfgV4>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
+      rc = launch_fwd<KK, 4, 1, MODE_CONV_ONLY, FwdCfgV4>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, zlo_zeroed);
     } else {
       int t = 0;
       if constexpr (KK == 4) t = tune_env("RHSEG_TUNE_FWD_S1");
@@ -752,9 +753,9 @@ static int level_fwd_impl(const float* feats, const float* eff_w, const float* e
         if (t == 1) rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, PipeCfg<8, 16, 3, 2>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
         else if (t == 2) rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, PipeCfg<8, 8, 4, 2>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
         else if (t == 3) rc = launch_fwd<KK, 1, 4, MODE_CONV_ONLY, PipeCfg<4, 16, 4, 1>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
-        else rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, FwdCfgS1>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
+        else rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, FwdCfgS1>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, zlo_zeroed);
       } else {
-        rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, FwdCfgS1>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
+        rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, FwdCfgS1>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, zlo_zeroed);
       }
     }
     if (rc != RHSEG_OK) return rc;
@@ -781,17 +782,17 @@ extern "C" int rhseg_head_level_fwd_eval(const float* feats, const float* eff_w,
                                          float* probs, double* psum, const float* targets, long t_bstride,
                                          long t_cstride, const float* parent_targets, long pt_bstride, long pt_cstride,
                                          const unsigned char* prev_idx, void* out_words, unsigned char* idx_out,
-                                         void* stream) {
+                                         int flags, void* stream) {
   if (!targets || !out_words) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   const int child = act_mode == RHSEG_ACT_SIGMOID ? 0 : 1;
   const int nc = child ? K + 1 : K;
   const size_t words = (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K + (size_t)nc * nc;
-  RHSEG_CUDA(cudaMemsetAsync(out_words, 0, words * 8, (cudaStream_t)stream));
+  if (!(flags & RHSEG_EVAL_PREZEROED)) RHSEG_CUDA(cudaMemsetAsync(out_words, 0, words * 8, (cudaStream_t)stream));
   double* stats = reinterpret_cast<double*>(out_words);
   double* cons = stats + (size_t)B * K * RHSEG_NSTAT;
   EvalArgs ea{targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, child, stats, cons,
               reinterpret_cast<unsigned long long*>(cons + RHSEG_MAX_K), idx_out};
   return level_fwd_impl(feats, eff_w, eff_b, prev_probs, table, B, C, Hf, Wf, H, W, K, K_prev, act_mode, z_lo, logits, probs,
-                        psum, 0, stream, &ea);
+                        psum, (flags & 2), stream, &ea);
 }

@@ -2,6 +2,7 @@
 // Metrics/performance_metrics.py:27-141) and the train-loop prediction glue
 // (train.py:206-231, predictEval.py:409-422).
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "eval_accum.cuh"
 
@@ -147,8 +148,8 @@ __global__ void metric_ratios_kernel(const long long* __restrict__ conf, int nc,
 // so neither the one-hot tensors nor the eval targets are ever materialised.
 // out layout (8-byte words): [B*K*5 fp64 stats][RHSEG_MAX_K fp64 consistency sums][nc*nc int64 confusion]
 // ------------------------------------------------------------------------------------
-template <int K, int VEC, int ITER, int THREADS>
-__global__ void __launch_bounds__(THREADS, 2)
+template <int K, int VEC, int MINB, int THREADS>
+__global__ void __launch_bounds__(THREADS, MINB)
 level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ targets, long t_bstride, long t_cstride,
                   const float* __restrict__ parent_targets, long pt_bstride, long pt_cstride,
                   const unsigned char* __restrict__ prev_idx, const int32_t* __restrict__ table, long N, int child,
@@ -314,32 +315,38 @@ extern "C" int rhseg_metric_ratios(const int64_t* conf, int nc, float* out5, voi
 extern "C" int rhseg_level_eval(const float* logits, const float* targets, long t_bstride, long t_cstride,
                                 const float* parent_targets, long pt_bstride, long pt_cstride,
                                 const unsigned char* prev_idx, const int32_t* table, int B, int K, int n_pix,
-                                int child, void* out_words, unsigned char* idx_out, int ctas_per_sm, void* stream) {
+                                int child, void* out_words, unsigned char* idx_out, int flags, void* stream) {
   if (!logits || !targets || !out_words || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   if (child && !table) return RHSEG_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int nc = child ? K + 1 : K;
   const size_t words = (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K + (size_t)nc * nc;
-  RHSEG_CUDA(cudaMemsetAsync(out_words, 0, words * 8, st));
+  if (!(flags & RHSEG_EVAL_PREZEROED)) RHSEG_CUDA(cudaMemsetAsync(out_words, 0, words * 8, st));
   double* stats = reinterpret_cast<double*>(out_words);
   double* cons = stats + (size_t)B * K * RHSEG_NSTAT;
   unsigned long long* conf = reinterpret_cast<unsigned long long*>(cons + RHSEG_MAX_K);
   const long N = n_pix;
-  constexpr int THREADS = 256, ITER = 1;
-  // CTAs per sample for one resident wave; ctas_per_sm = 1 leaves room for a concurrently running kernel
-  const int slots = std::max(1, device_sm_count() * (ctas_per_sm == 1 ? 1 : 2) / B);
+  constexpr int THREADS = 256;
+  static int tune = -1;
+  if (tune < 0) { const char* e = getenv("RHSEG_TUNE_EVAL"); tune = e ? atoi(e) : 0; }
+  const int per_sm = tune == 1 ? 3 : 2;
+  const int slots = std::max(1, device_sm_count() * per_sm / B);  // CTAs per sample for one resident wave
   bool v4 = (N % 4 == 0) && aligned16(logits) && aligned16(targets) && t_bstride % 4 == 0 && t_cstride % 4 == 0 &&
             (reinterpret_cast<uintptr_t>(prev_idx) % 4 == 0) && (reinterpret_cast<uintptr_t>(idx_out) % 4 == 0);
   if (parent_targets) v4 = v4 && aligned16(parent_targets) && pt_bstride % 4 == 0 && pt_cstride % 4 == 0;
   RHSEG_DISPATCH_K(K, {
     if (v4) {
       dim3 grid((unsigned)std::min<long>(slots, (N + THREADS * 4 - 1) / (THREADS * 4)), B);
-      level_eval_kernel<KK, 4, ITER, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
-          pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
+      if (tune == 1)
+        level_eval_kernel<KK, 4, 3, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
+            pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
+      else
+        level_eval_kernel<KK, 4, 2, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
+            pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     } else {
       dim3 grid((unsigned)std::min<long>(slots, (N + THREADS - 1) / THREADS), B);
-      level_eval_kernel<KK, 1, ITER, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
+      level_eval_kernel<KK, 1, 2, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
           pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     }
   });

@@ -74,7 +74,7 @@ class _FusedStepFn(torch.autograd.Function):
         for k in tree.head_channels:
             ch_off.append(ch_off[-1] + k)
         offs, words = _eval_layout(tree, B)
-        ws = torch.empty((words,), dtype=torch.float64, device=dev)
+        ws = torch.zeros((words,), dtype=torch.float64, device=dev)  # one fill; the eval kernels are told it is zeroed
         idx_maps = [torch.empty((B,) + tuple(target.shape[2:]), dtype=torch.uint8, device=dev) if L < n - 1 else None
                     for L in range(n)]
 

@@ -61,6 +61,9 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
     psum_all = torch.zeros((sum(tree.head_channels) * B,), dtype=torch.float64, device=dev)
     psum_off = 0
     used_side = False
+    # low-res logits of all levels in one zero-filled buffer (tiles split between CTAs accumulate into it)
+    zlo_all = torch.zeros((B * sum(tree.head_channels) * Hf * Wf,), dtype=torch.float32, device=dev) if upsampled else None
+    zlo_off = 0
     for L in range(n):
         K = tree.head_channels[L]
         K_prev = tree.head_channels[L - 1] if L > 0 else 0
@@ -81,7 +84,10 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
         p = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
         psum = psum_all[psum_off:psum_off + B * K].view(B, K)
         psum_off += B * K
-        z_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev) if upsampled else None
+        z_lo = None
+        if upsampled:
+            z_lo = zlo_all[zlo_off:zlo_off + B * K * Hf * Wf].view(B, K, Hf, Wf)
+            zlo_off += B * K * Hf * Wf
         ev = evaluate(L, (B, C, Hf, Wf, H, W)) if evaluate is not None else None
         # The evaluation of level L only needs its logits (and the previous level's index map): for all
         # but the last level it runs on a side stream, overlapping the (memory-bound) forward of the next
@@ -95,11 +101,11 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
             call("rhseg_head_level_fwd_eval", ptr(f), ptr(eff_w), ptr(eff_b),
                  ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
                  B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum),
-                 t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, words_ptr, idx_ptr, st)
+                 t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, words_ptr, idx_ptr, 1 | 2, st)
         else:
             call("rhseg_head_level_fwd", ptr(f), ptr(eff_w), ptr(eff_b),
                  ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
-                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum), 0, st)
+                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum), 2 if upsampled else 0, st)
             if ev is not None:
                 t_ptr, t_bs, t_cs, pt_ptr, pidx_ptr, words_ptr, idx_ptr = ev
                 if overlap:
@@ -107,14 +113,14 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
                     side = _side_stream(dev)
                     side.wait_stream(main)  # logits of this level (and everything before) are ready
                     call("rhseg_level_eval", ptr(z), t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, ptr(tables[L]),
-                         B, K, n_pix, 1 if L > 0 else 0, words_ptr, idx_ptr, 2, side.cuda_stream)
+                         B, K, n_pix, 1 if L > 0 else 0, words_ptr, idx_ptr, 1, side.cuda_stream)
                     used_side = True
                 else:
                     if used_side:  # the previous level's index map is produced on the side stream
                         torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
                         used_side = False
                     call("rhseg_level_eval", ptr(z), t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, ptr(tables[L]),
-                         B, K, n_pix, 1 if L > 0 else 0, words_ptr, idx_ptr, 2, st)
+                         B, K, n_pix, 1 if L > 0 else 0, words_ptr, idx_ptr, 1, st)
         probs.append(p); logits.append(z); psums.append(psum); eff_ws.append(eff_w); gbs.append(gb)
     if used_side:
         torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))

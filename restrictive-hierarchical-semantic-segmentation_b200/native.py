@@ -29,7 +29,7 @@ SIGNATURES = {
     "rhseg_film_fold": [_P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _P, _P, _P, _P],
     "rhseg_head_level_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P],
     "rhseg_head_level_fwd_eval": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P,
-                                  _P, _L, _L, _P, _L, _L, _P, _P, _P, _P],
+                                  _P, _L, _L, _P, _L, _L, _P, _P, _P, _I, _P],
     "rhseg_head_act_bwd": [_P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "rhseg_upsample_adjoint": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "rhseg_head_dz_lowres_fused": [_P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
