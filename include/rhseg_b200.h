@@ -283,6 +283,12 @@ int rhseg_level_eval(const float* logits, const float* targets, long t_bstride, 
 int rhseg_stitch_levels(const float* leaves, int B, int n_leaves, int n_pix, const uint32_t* masks,
                         int n_out, float* out, void* stream);
 
+/* out [B, c_image+K, n_pix] = cat([image [B,c_image,n_pix], logits [B,K,n_pix]], dim=1).  Stand-alone
+ * utility (north_star item 2): the reference itself never concatenates, so nothing in
+ * the forward path calls it.                                                                    */
+int rhseg_concat_image_logits(const float* image, int c_image, const float* logits, int K, int B, int n_pix,
+                              float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -377,3 +377,35 @@ extern "C" int rhseg_stitch_levels(const float* leaves, int B, int n_leaves, int
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// Image (+) logits concat (north_star item 2, SURVEY row a4'): out = cat([image, logits], dim=1).
+// The reference never performs this concat (its recurrent passes re-run the donor on the unchanged
+// image, Models/models.py:277, :773), so it is a stand-alone utility and is not wired into forward.
+// ------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256)
+concat_planes_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, long N,
+                     float* __restrict__ out) {
+  const int plane = blockIdx.y;              // (sample, output channel)
+  const int c_out = ca + cb;
+  const int s = plane / c_out, c = plane - s * c_out;
+  const float* src = c < ca ? a + ((size_t)s * ca + c) * N : b + ((size_t)s * cb + (c - ca)) * N;
+  float* dst = out + (size_t)plane * N;
+  for (long px = ((long)blockIdx.x * 256 + threadIdx.x) * VEC; px < N; px += (long)gridDim.x * 256 * VEC)
+    st_stream<VEC>(dst + px, ld_stream<VEC>(src + px));
+}
+
+extern "C" int rhseg_concat_image_logits(const float* image, int c_image, const float* logits, int K, int B, int n_pix,
+                                         float* out, void* stream) {
+  if (!image || !logits || !out || B <= 0 || c_image < 1 || K < 1 || n_pix <= 0) return RHSEG_ERR_ARG;
+  const long N = n_pix;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool v4 = N % 4 == 0 && aligned16(image) && aligned16(logits) && aligned16(out);
+  const long per = v4 ? 1024 : 256;
+  dim3 grid((unsigned)std::min<long>(64, (N + per - 1) / per), (unsigned)(B * (c_image + K)));
+  if (v4) concat_planes_kernel<4><<<grid, 256, 0, st>>>(image, c_image, logits, K, N, out);
+  else concat_planes_kernel<1><<<grid, 256, 0, st>>>(image, c_image, logits, K, N, out);
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}

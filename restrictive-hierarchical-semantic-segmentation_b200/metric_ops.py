@@ -114,3 +114,16 @@ def stitch_flat_to_levels(flat, tree):
         levels.append(out[:, s:s + k])
         s += k
     return levels
+
+
+def concat_image_logits(image, logits):
+    """cat([image, logits], dim=1) as one kernel (stand-alone utility; not part of the reference forward)."""
+    native.require_cuda(image, logits)
+    a = image.float().contiguous()
+    b = logits.float().contiguous()
+    if a.shape[0] != b.shape[0] or tuple(a.shape[2:]) != tuple(b.shape[2:]):
+        raise native.NativeError("image %s and logits %s do not share batch / spatial size" % (tuple(a.shape), tuple(b.shape)))
+    B, ca, H, W = a.shape
+    out = torch.empty((B, ca + b.shape[1], H, W), dtype=torch.float32, device=a.device)
+    call("rhseg_concat_image_logits", ptr(a), ca, ptr(b), b.shape[1], B, H * W, ptr(out), stream_of(a))
+    return out

@@ -126,3 +126,13 @@ def test_flat_to_hierarchy_stitching(tree_dict):
         assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in want]
         for a, b in zip(got, want):
             assert torch.equal(a.cpu(), b)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 4, 9, 11), (1, 1, 8, 16, 24)])
+def test_concat_image_logits_utility(shape):
+    import rhseg_b200
+    B, ci, K, H, W = shape
+    g = torch.Generator().manual_seed(1)
+    x, z = torch.randn(B, ci, H, W, generator=g), torch.randn(B, K, H, W, generator=g)
+    got = rhseg_b200.concat_image_logits(x.to(DEV), z.to(DEV))
+    assert torch.equal(got.cpu(), torch.cat([x, z], dim=1))
