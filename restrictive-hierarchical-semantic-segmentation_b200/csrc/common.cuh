@@ -51,6 +51,16 @@ inline int device_sm_count() {
   return cached;
 }
 
+// Persistent grid for `units` equal work items and `slots` resident CTAs: the smallest grid that keeps the
+// per-CTA iteration count at its minimum, so that every CTA runs the same number of iterations (+-1 unit)
+// instead of a few CTAs running one extra.
+inline int balanced_grid(long units, long slots) {
+  if (units <= 0) return 1;
+  if (slots < 1) slots = 1;
+  const long iters = (units + slots - 1) / slots;
+  return (int)((units + iters - 1) / iters);
+}
+
 __host__ __device__ constexpr int pad_k(int K) { return K <= 1 ? 1 : (K <= 2 ? 2 : (K <= 4 ? 4 : 8)); }
 __host__ __device__ constexpr int log2_pow2(int v) { return v <= 1 ? 0 : 1 + log2_pow2(v / 2); }
 

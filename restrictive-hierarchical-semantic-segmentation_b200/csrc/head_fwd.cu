@@ -668,12 +668,12 @@ static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32
     const int slots = std::max(1, device_sm_count() * 2 / B);  // CTAs per sample: one resident wave at 2 CTAs/SM
     if (v4) {
       const int tiles_x = (W + 63) / 64, tiles = tiles_x * ((H + 15) / 16);
-      dim3 grid(std::min(slots, tiles), B);
+      dim3 grid(balanced_grid(tiles, slots), B);
       if (ea) upsample_act_tiled_kernel<K, 4, MODE, true><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
       else upsample_act_tiled_kernel<K, 4, MODE, false><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
     } else {
       const int tiles_x = (W + 15) / 16, tiles = tiles_x * ((H + 15) / 16);
-      dim3 grid(std::min(slots, tiles), B);
+      dim3 grid(balanced_grid(tiles, slots), B);
       if (ea) upsample_act_tiled_kernel<K, 1, MODE, true><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
       else upsample_act_tiled_kernel<K, 1, MODE, false><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
     }

@@ -179,13 +179,22 @@ __device__ __forceinline__ SampleLoss sample_loss(const double* __restrict__ st,
   SampleLoss r;
   double ce = 0.0, I = 0.0, U = 0.0;
   bool ce_nan = false;
-  for (int c = 0; c < K; ++c) {
-    const double w = (double)weights[c];
-    const double cnt = st[c * NS + 1];
-    if (cnt == 0.0) ce_nan = true;
-    else ce += -(w * st[c * NS + 0]) / cnt;
-    I += w * st[c * NS + 2];
-    U += w * st[c * NS + 3] + w * st[c * NS + 4];
+  // fixed trip count + predicate: all loads of the sample are issued together (this kernel is pure latency)
+  double sv[RHSEG_KERNEL_MAX_K][NS], wv[RHSEG_KERNEL_MAX_K];
+#pragma unroll
+  for (int c = 0; c < RHSEG_KERNEL_MAX_K; ++c) {
+    wv[c] = c < K ? (double)weights[c] : 0.0;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) sv[c][j] = c < K ? st[c * NS + j] : 1.0;
+  }
+#pragma unroll
+  for (int c = 0; c < RHSEG_KERNEL_MAX_K; ++c) {
+    if (c < K) {
+      if (sv[c][1] == 0.0) ce_nan = true;
+      else ce += -(wv[c] * sv[c][0]) / sv[c][1];
+      I += wv[c] * sv[c][2];
+      U += wv[c] * sv[c][3] + wv[c] * sv[c][4];
+    }
   }
   ce = ce / (double)K;
   if (ce != ce) ce_nan = true;
@@ -195,12 +204,13 @@ __device__ __forceinline__ SampleLoss sample_loss(const double* __restrict__ st,
   r.ce = ce_nan ? 1.0 : ce;
   r.dice_ok = !(dl != dl);
   r.dice = r.dice_ok ? dl : 0.0;
-  for (int c = 0; c < K; ++c) {
-    const double w = (double)weights[c];
-    const double cnt = st[c * NS + 1];
-    cf[c * 3 + 0] = ce_nan ? 0.f : (float)(-w / (cnt * (double)K * (double)B));
-    cf[c * 3 + 1] = r.dice_ok ? (float)(w * (-2.0 / den)) : 0.f;   // scaled by 1/n_valid afterwards
-    cf[c * 3 + 2] = r.dice_ok ? (float)(w * (num / (den * den))) : 0.f;
+#pragma unroll
+  for (int c = 0; c < RHSEG_KERNEL_MAX_K; ++c) {
+    if (c < K) {
+      cf[c * 3 + 0] = ce_nan ? 0.f : (float)(-wv[c] / (sv[c][1] * (double)K * (double)B));
+      cf[c * 3 + 1] = r.dice_ok ? (float)(wv[c] * (-2.0 / den)) : 0.f;   // scaled by 1/n_valid afterwards
+      cf[c * 3 + 2] = r.dice_ok ? (float)(wv[c] * (num / (den * den))) : 0.f;
+    }
   }
   return r;
 }
@@ -224,8 +234,11 @@ step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ we
       r_off[L + 1] = r_off[L] + 5 * (size_t)nc;
     }
   }
+  __shared__ double cons_sm[RHSEG_MAX_LEVELS];
   if (tid < RHSEG_MAX_LEVELS * 4) (&acc[0][0])[tid] = 0.0;
+  if (tid < RHSEG_MAX_LEVELS) cons_sm[tid] = 0.0;
   __syncthreads();
+  // (1) per-sample losses: thread <-> (level, sample)
   for (int e = tid; e < nL * B; e += blockDim.x) {
     const int L = e / B, b = e - L * B, K = lv.K[L];
     const SampleLoss r = sample_loss(ws + w_off[L] + (size_t)b * K * RHSEG_NSTAT, weights + k_off[L], K, B, smooth,
@@ -234,24 +247,22 @@ step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ we
     if (r.dice_ok) { atomicAdd(&acc[L][1], r.dice); atomicAdd(&acc[L][2], 1.0); }
     if (!r.ce_nan) atomicAdd(&acc[L][3], 1.0);
   }
-  __syncthreads();
-  // dice coefficients carry 1/n_valid of their level
-  for (int L = 0; L < nL; ++L) {
-    const float inv_nv = acc[L][2] > 0.0 ? (float)(1.0 / acc[L][2]) : 0.f;
-    float* cf = coef + c_off[L];
-    for (int i = tid; i < B * lv.K[L]; i += blockDim.x) {
-      cf[(size_t)i * 3 + 1] *= inv_nv;
-      cf[(size_t)i * 3 + 2] *= inv_nv;
-    }
-  }
-  // the five per-class ratios of every level (same arithmetic as rhseg_metric_ratios)
-  for (int L = 0; L < nL; ++L) {
-    const int K = lv.K[L], nc = lv.child[L] ? K + 1 : K;
-    if (tid < nc) {
+  // (2) concurrently, from the top of the block: the five per-class ratios, thread <-> (level, class)
+  {
+    int e = (int)blockDim.x - 1 - tid, L = 0;
+    while (L < nL && e >= (lv.child[L] ? lv.K[L] + 1 : lv.K[L])) { e -= (lv.child[L] ? lv.K[L] + 1 : lv.K[L]); ++L; }
+    if (L < nL) {
+      const int K = lv.K[L], nc = lv.child[L] ? K + 1 : K, c = e;
       const long long* conf = reinterpret_cast<const long long*>(ws + w_off[L] + (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K);
-      const int c = tid;
+      long long rowv[RHSEG_KERNEL_MAX_K + 1], colv[RHSEG_KERNEL_MAX_K + 1];
+#pragma unroll
+      for (int j = 0; j <= RHSEG_KERNEL_MAX_K; ++j) {
+        rowv[j] = j < nc ? conf[c * nc + j] : 0;
+        colv[j] = j < nc ? conf[j * nc + c] : 0;
+      }
       long long tp = conf[c * nc + c], row = 0, col = 0;
-      for (int j = 0; j < nc; ++j) { row += conf[c * nc + j]; col += conf[j * nc + c]; }
+#pragma unroll
+      for (int j = 0; j <= RHSEG_KERNEL_MAX_K; ++j) { row += rowv[j]; col += colv[j]; }
       const long long fp = col - tp, fn = row - tp;
       auto safe = [](float num, float den) { return num / (den == 0.f ? 1.f : den); };
       const float tpf = (float)tp, fpf = (float)fp, fnf = (float)fn;
@@ -263,13 +274,27 @@ step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ we
       o[4 * nc + c] = safe(tpf, (float)(tp + fn));
     }
   }
+  // (3) concurrently: consistency sums, thread <-> (level, group) in the middle of the block
+  if (tid >= 64 && tid < 64 + nL * RHSEG_MAX_K) {
+    const int L = (tid - 64) / RHSEG_MAX_K, g = (tid - 64) % RHSEG_MAX_K;
+    if (g < lv.G[L]) atomicAdd(&cons_sm[L], (ws + w_off[L] + (size_t)B * lv.K[L] * RHSEG_NSTAT)[g] * inv_bn);
+  }
+  __syncthreads();
+  // dice coefficients carry 1/n_valid of their level
+  for (int L = 0; L < nL; ++L) {
+    const float inv_nv = acc[L][2] > 0.0 ? (float)(1.0 / acc[L][2]) : 0.f;
+    float* cf = coef + c_off[L];
+    for (int i = tid; i < B * lv.K[L]; i += blockDim.x) {
+      cf[(size_t)i * 3 + 1] *= inv_nv;
+      cf[(size_t)i * 3 + 2] *= inv_nv;
+    }
+  }
   if (tid == 0) {
     double cons_total = 0.0;
     int cons_count = 0;
     float total = 0.f;
     for (int L = 0; L < nL; ++L) {
-      const double* cons = ws + w_off[L] + (size_t)B * lv.K[L] * RHSEG_NSTAT;
-      for (int g = 0; g < lv.G[L]; ++g) cons_total += cons[g] * inv_bn;  // mean |children - parent| of group g
+      cons_total += cons_sm[L];  // sum over groups of mean |children - parent|
       cons_count += lv.G[L];
       const float ce = (float)(acc[L][0] / (double)B);
       const float dice = acc[L][2] > 0.0 ? (float)(acc[L][1] / acc[L][2]) : 0.f;

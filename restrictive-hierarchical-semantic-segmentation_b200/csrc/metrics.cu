@@ -337,7 +337,7 @@ extern "C" int rhseg_level_eval(const float* logits, const float* targets, long 
   if (parent_targets) v4 = v4 && aligned16(parent_targets) && pt_bstride % 4 == 0 && pt_cstride % 4 == 0;
   RHSEG_DISPATCH_K(K, {
     if (v4) {
-      dim3 grid((unsigned)std::min<long>(slots, (N + THREADS * 4 - 1) / (THREADS * 4)), B);
+      dim3 grid((unsigned)balanced_grid((N + THREADS * 4 - 1) / (THREADS * 4), slots), B);
       if (tune == 1)
         level_eval_kernel<KK, 4, 3, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
             pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
@@ -345,7 +345,7 @@ extern "C" int rhseg_level_eval(const float* logits, const float* targets, long 
         level_eval_kernel<KK, 4, 2, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
             pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     } else {
-      dim3 grid((unsigned)std::min<long>(slots, (N + THREADS - 1) / THREADS), B);
+      dim3 grid((unsigned)balanced_grid((N + THREADS - 1) / THREADS, slots), B);
       level_eval_kernel<KK, 1, 2, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
           pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     }

@@ -9,6 +9,7 @@
 // SRC 1: dz_hi is formed on the fly per hi-res pixel as  loss gradient (closed form from logits,
 //        targets, coefficients) + activation backward (sigmoid / restrictive softmax with the
 //        gradient arriving at the probabilities), so the hi-res gradient tensor never exists.
+#include <algorithm>
 #include "common.cuh"
 
 namespace rhseg {
@@ -189,11 +190,11 @@ upsample_adjoint_tiled_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, i
 // into tmpx [B,K,H,Wf]; pass 2 reduces tmpx along y.  Used when W % 4 == 0 and the taps per low-res
 // index fit XR_MAXW; the tiled kernel above is the generic fallback.
 // ------------------------------------------------------------------------------------
-constexpr int XR_ROWS = 4, XR_THREADS = 256, XR_MAXW = 12;
+constexpr int XR_MAXROWS = 8, XR_THREADS = 256, XR_MAXW = 12;
 
 template <int K, int SRC, int MODE>
 __global__ void __launch_bounds__(XR_THREADS)
-dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, int H, int W, float sx,
+dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, int H, int W, float sx, int XR_ROWS,
                        float* __restrict__ tmpx) {
   extern __shared__ __align__(16) float sm[];
   const int Wp = W + 4;
@@ -202,8 +203,6 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
   int* wstart = reinterpret_cast<int*>(wtab + (size_t)Wf * XR_MAXW);  // [Wf]
   int* wcnt = wstart + Wf;                           // [Wf]
   const int b = blockIdx.y, tid = threadIdx.x;
-  const int y0 = blockIdx.x * XR_ROWS;
-  const int rows = min(XR_ROWS, H - y0);
   const long N = (long)H * W;
 
   for (int j = tid; j < Wf; j += XR_THREADS) {
@@ -222,8 +221,12 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
     wcnt[j] = cnt < XR_MAXW ? cnt : XR_MAXW;
   }
 
-  // ---- phase 1: gradient of ROWS full rows -> shared memory (4 pixels per thread and step) ----
+  // persistent over the sample's row blocks (the weight tables above are built once per CTA)
   const int vec_per_row = W / 4;
+  for (int y0 = blockIdx.x * XR_ROWS; y0 < H; y0 += gridDim.x * XR_ROWS) {
+  const int rows = min(XR_ROWS, H - y0);
+  __syncthreads();  // tables ready / previous block's readers done
+  // ---- phase 1: gradient of ROWS full rows -> shared memory (4 pixels per thread and step) ----
   if constexpr (SRC == 0) {
     for (int e = tid; e < rows * vec_per_row; e += XR_THREADS) {
       const int r = e / vec_per_row, xv = (e - r * vec_per_row) * 4;
@@ -318,6 +321,7 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
     for (int q = 0; q < n; ++q) acc = fmaf(wt[q], row[q], acc);
     tmpx[(((size_t)b * K + k) * H + y0 + r) * Wf + j] = acc;
   }
+  }  // row blocks
 }
 
 // pass 2: dz_lo[b][k][i][j] = sum_y wy(y, i) tmpx[b][k][y][j]
@@ -435,12 +439,17 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
     if (SRC == 0) rows_ok = rows_ok && al(dz_hi);
     else rows_ok = rows_ok && al(fa.logits) && al(fa.targets) && fa.t_bstride % 4 == 0 && fa.t_cstride % 4 == 0 &&
                    al(fa.prev_probs) && al(fa.dp_pix) && al(fa.dp_prev);
-    const size_t smem = ((size_t)K * XR_ROWS * (W + 4) + (size_t)Wf * XR_MAXW + 2 * (size_t)Wf) * sizeof(float);
-    if (rows_ok && smem <= 160 * 1024) {
-      auto kern = dz_rows_xreduce_kernel<K, SRC, MODE>;
+    auto kern = dz_rows_xreduce_kernel<K, SRC, MODE>;
+    constexpr int ROWS = 2;  // rows per block: small blocks, the persistent loop balances them over one wave
+    const size_t smem = ((size_t)K * ROWS * (W + 4) + (size_t)Wf * XR_MAXW + 2 * (size_t)Wf) * sizeof(float);
+    if (rows_ok && smem <= 200 * 1024) {
       if (smem > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      dim3 grid((H + XR_ROWS - 1) / XR_ROWS, B);
-      kern<<<grid, XR_THREADS, smem, st>>>(dz_hi, fa, Wf, H, W, sx, tmpx);
+      int per_sm = 0;
+      RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, XR_THREADS, smem));
+      if (per_sm < 1) per_sm = 1;
+      const long slots = std::max<long>(1, (long)per_sm * device_sm_count() / B);
+      dim3 grid(balanced_grid((H + ROWS - 1) / ROWS, slots), B);
+      kern<<<grid, XR_THREADS, smem, st>>>(dz_hi, fa, Wf, H, W, sx, ROWS, tmpx);
       RHSEG_LAUNCH_CHECK();
       const long total = (long)B * K * Hf * Wf;
       yreduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tmpx, Hf, Wf, H, sy, total, dz_lo);
