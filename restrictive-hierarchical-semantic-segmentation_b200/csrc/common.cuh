@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #pragma GCC visibility push(default)
 #include "rhseg_b200.h"
 #pragma GCC visibility pop
@@ -39,6 +40,37 @@
   }
 
 namespace rhseg {
+
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute and
+// begins with pdl_wait(): its CTAs may become resident (and pay launch latency / run setup code)
+// while the previous kernel of the stream drains, and block here until that kernel has completed
+// and its writes are visible.  RHSEG_NO_PDL=1 turns the attribute off (plain stream order).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("RHSEG_NO_PDL");
+    cached = (e && e[0] == '1') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // SM count of the current device (cached per process; grids are sized from it)
 inline int device_sm_count() {

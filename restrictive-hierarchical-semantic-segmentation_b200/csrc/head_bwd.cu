@@ -19,6 +19,7 @@ act_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ prev_
                const int32_t* __restrict__ table, const float* __restrict__ dz_in,
                const double* __restrict__ g_uniform, float inv_npix, const float* __restrict__ dp_pix,
                uint32_t pix_mask, int K_prev, long N, float* __restrict__ dz_out, float* __restrict__ dp_prev) {
+  pdl_wait();
   const int b = blockIdx.y;
   const long px = ((long)blockIdx.x * THREADS + threadIdx.x) * VEC;
   if (px >= N) return;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(CFG::THREADS)
 conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, const float* __restrict__ eff_w,
                 int C, int N, int n_tiles, int n_stages, long units_total, int a0, float* __restrict__ dfeats,
                 double* __restrict__ S, double* __restrict__ s) {
+  pdl_wait();
   constexpr int KP = pad_k(K);
   constexpr int P = J * VEC;
   constexpr int NCONS = CFG::CONSUMERS;
@@ -364,7 +366,7 @@ static int launch_conv_bwd(const float* feats, const float* dz, const float* eff
   const long units_total = (long)B * n_stages * n_tiles;
   const long grid = std::max<long>(1, std::min<long>((long)sm_count * per_sm, units_total));
   const int a0 = (int)((reinterpret_cast<uintptr_t>(feats) >> 2) & 3);
-  kern<<<(unsigned)grid, CFG::THREADS, smem, st>>>(feats, dz, eff_w, C, N, n_tiles, n_stages, units_total, a0, dfeats, S, s);
+  launch_pdl(kern, dim3((unsigned)grid), dim3(CFG::THREADS), smem, st, feats, dz, eff_w, C, N, n_tiles, n_stages, units_total, a0, dfeats, S, s);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }
@@ -390,6 +392,7 @@ param_grads_kernel(const double* __restrict__ S, const double* __restrict__ s, c
                    const double* __restrict__ prev_psum, double n_pix, int B, int C, int K, int K_prev,
                    float* __restrict__ d_head_w, float* __restrict__ d_head_b, float* __restrict__ d_film_w,
                    float* __restrict__ d_film_b, double* __restrict__ g_prev) {
+  pdl_wait();
   constexpr int NV = RHSEG_KERNEL_MAX_K + 2 + 2 * RHSEG_MAX_K;  // dw[k], dfb_g, dfb_b, dfw_g[j], dfw_b[j]
   __shared__ float red[PG_BL][PG_CH][NV + 1];
   __shared__ float gsm[PG_THREADS / 32];
@@ -494,19 +497,19 @@ extern "C" int rhseg_head_act_bwd(const float* logits, const float* prev_probs, 
     if (N % 4 == 0) {
       dim3 grid((unsigned)((N / 4 + THREADS - 1) / THREADS), B);
       if (act_mode == RHSEG_ACT_SIGMOID)
-        act_bwd_kernel<KK, 4, RHSEG_ACT_SIGMOID, THREADS><<<grid, THREADS, 0, st>>>(logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
+        launch_pdl(act_bwd_kernel<KK, 4, RHSEG_ACT_SIGMOID, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
       else if (act_mode == RHSEG_ACT_GROUPED)
-        act_bwd_kernel<KK, 4, RHSEG_ACT_GROUPED, THREADS><<<grid, THREADS, 0, st>>>(logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
+        launch_pdl(act_bwd_kernel<KK, 4, RHSEG_ACT_GROUPED, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
       else
-        act_bwd_kernel<KK, 4, RHSEG_ACT_ZEROS, THREADS><<<grid, THREADS, 0, st>>>(logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
+        launch_pdl(act_bwd_kernel<KK, 4, RHSEG_ACT_ZEROS, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
     } else {
       dim3 grid((unsigned)((N + THREADS - 1) / THREADS), B);
       if (act_mode == RHSEG_ACT_SIGMOID)
-        act_bwd_kernel<KK, 1, RHSEG_ACT_SIGMOID, THREADS><<<grid, THREADS, 0, st>>>(logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
+        launch_pdl(act_bwd_kernel<KK, 1, RHSEG_ACT_SIGMOID, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
       else if (act_mode == RHSEG_ACT_GROUPED)
-        act_bwd_kernel<KK, 1, RHSEG_ACT_GROUPED, THREADS><<<grid, THREADS, 0, st>>>(logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
+        launch_pdl(act_bwd_kernel<KK, 1, RHSEG_ACT_GROUPED, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
       else
-        act_bwd_kernel<KK, 1, RHSEG_ACT_ZEROS, THREADS><<<grid, THREADS, 0, st>>>(logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
+        launch_pdl(act_bwd_kernel<KK, 1, RHSEG_ACT_ZEROS, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, prev_probs, table, dz_in, g_uniform, inv, dp_pix, pix_mask, K_prev, N, dz_out, dp_prev);
     }
   });
   RHSEG_LAUNCH_CHECK();
@@ -558,7 +561,7 @@ extern "C" int rhseg_head_param_grads(const double* S, const double* s, const fl
     if (K_prev < 1 || K_prev > RHSEG_MAX_K) return RHSEG_ERR_UNSUPPORTED;
     RHSEG_CUDA(cudaMemsetAsync(g_prev, 0, sizeof(double) * (size_t)B * K_prev, st));
   }
-  param_grads_kernel<<<(C + PG_CH - 1) / PG_CH, PG_THREADS, 0, st>>>(S, s, head_w, film_w, gamma_beta, prev_psum, n_pix, B, C, K, K_prev,
+  launch_pdl(param_grads_kernel, dim3((C + PG_CH - 1) / PG_CH), dim3(PG_THREADS), 0, st, S, s, head_w, film_w, gamma_beta, prev_psum, n_pix, B, C, K, K_prev,
                                                       d_head_w, d_head_b, d_film_w, d_film_b, g_prev);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;

@@ -18,6 +18,7 @@ __global__ void film_fold_kernel(const float* __restrict__ head_w, const float* 
                                  const double* __restrict__ prev_psum, double n_pix, int C, int K, int K_prev,
                                  float* __restrict__ gamma_beta, float* __restrict__ eff_w,
                                  float* __restrict__ eff_b) {
+  pdl_wait();
   extern __shared__ float sm[];  // cond[K_prev] | beta-dot partials[K * nwarps]
   const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
   float* cond = sm;
@@ -132,6 +133,7 @@ head_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ eff_w
                 const int32_t* __restrict__ table, int C, int N, int K_prev, int n_tiles, int n_stages,
                 long units_total, int a0, float* __restrict__ logits, float* __restrict__ probs,
                 double* __restrict__ psum) {
+  pdl_wait();
   constexpr int KP = pad_k(K);
   constexpr int P = J * VEC;
   constexpr int NCONS = CFG::CONSUMERS;
@@ -394,6 +396,7 @@ upsample_act_kernel(const float* __restrict__ z_lo, const float* __restrict__ pr
                     const int32_t* __restrict__ table, int Hf, int Wf, int H, int W, int K_prev,
                     float sy, float sx, long total_vec, float* __restrict__ logits,
                     float* __restrict__ probs, double* __restrict__ psum, int vec_per_sample) {
+  pdl_wait();
   __shared__ float red[(THREADS / 32) * K];
   const int b = blockIdx.y;
   const long vi = (long)blockIdx.x * THREADS + threadIdx.x;  // vector index inside the sample
@@ -490,6 +493,7 @@ upsample_act_tiled_kernel(const float* __restrict__ z_lo, const float* __restric
                           const int32_t* __restrict__ table, int Hf, int Wf, int H, int W, int K_prev, float sy,
                           float sx, int tiles_x, int tiles_per_sample, float* __restrict__ logits,
                           float* __restrict__ probs, double* __restrict__ psum, EvalArgs ea) {
+  pdl_wait();
   constexpr int TH = 16, TW = 16 * VEC;
   constexpr int PH = TH + 2, PW = TW + 2;  // patch bound for scale <= 1
   __shared__ float patch[K][PH][PW];
@@ -617,7 +621,7 @@ static int launch_fwd(const float* feats, const float* eff_w, const float* eff_b
   if (MODE == MODE_CONV_ONLY && grid > 1 && !out_prezeroed)
     RHSEG_CUDA(cudaMemsetAsync(logits, 0, sizeof(float) * (size_t)B * K * N, st));
   const int a0 = (int)((reinterpret_cast<uintptr_t>(feats) >> 2) & 3);
-  kern<<<(unsigned)grid, CFG::THREADS, smem, st>>>(feats, eff_w, eff_b, prev_probs, table, C, N, K_prev, n_tiles, n_stages,
+  launch_pdl(kern, dim3((unsigned)grid), dim3(CFG::THREADS), smem, st, feats, eff_w, eff_b, prev_probs, table, C, N, K_prev, n_tiles, n_stages,
                                                   units_total, a0, logits, probs, psum);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
@@ -669,13 +673,13 @@ static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32
     if (v4) {
       const int tiles_x = (W + 63) / 64, tiles = tiles_x * ((H + 15) / 16);
       dim3 grid(balanced_grid(tiles, slots), B);
-      if (ea) upsample_act_tiled_kernel<K, 4, MODE, true><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
-      else upsample_act_tiled_kernel<K, 4, MODE, false><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
+      if (ea) launch_pdl(upsample_act_tiled_kernel<K, 4, MODE, true>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
+      else launch_pdl(upsample_act_tiled_kernel<K, 4, MODE, false>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
     } else {
       const int tiles_x = (W + 15) / 16, tiles = tiles_x * ((H + 15) / 16);
       dim3 grid(balanced_grid(tiles, slots), B);
-      if (ea) upsample_act_tiled_kernel<K, 1, MODE, true><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
-      else upsample_act_tiled_kernel<K, 1, MODE, false><<<grid, 256, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
+      if (ea) launch_pdl(upsample_act_tiled_kernel<K, 1, MODE, true>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
+      else launch_pdl(upsample_act_tiled_kernel<K, 1, MODE, false>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
     }
     RHSEG_LAUNCH_CHECK();
     return RHSEG_OK;
@@ -684,12 +688,12 @@ static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32
   if (W % 4 == 0) {
     const int vps = H * (W / 4);
     dim3 grid((vps + THREADS - 1) / THREADS, B);
-    upsample_act_kernel<K, 4, MODE, THREADS><<<grid, THREADS, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev,
+    launch_pdl(upsample_act_kernel<K, 4, MODE, THREADS>, dim3(grid), dim3(THREADS), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev,
                                                                        sy, sx, 0, logits, probs, psum, vps);
   } else {
     const int vps = H * W;
     dim3 grid((vps + THREADS - 1) / THREADS, B);
-    upsample_act_kernel<K, 1, MODE, THREADS><<<grid, THREADS, 0, st>>>(z_lo, prev_probs, table, Hf, Wf, H, W, K_prev,
+    launch_pdl(upsample_act_kernel<K, 1, MODE, THREADS>, dim3(grid), dim3(THREADS), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev,
                                                                        sy, sx, 0, logits, probs, psum, vps);
   }
   RHSEG_LAUNCH_CHECK();
@@ -711,7 +715,7 @@ extern "C" int rhseg_film_fold(const float* head_w, const float* head_b, const f
   }
   const int threads = C >= 512 ? 768 : 256;
   const size_t smem = (RHSEG_MAX_K + RHSEG_KERNEL_MAX_K * (threads / 32)) * sizeof(float);
-  film_fold_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(head_w, head_b, film_w, film_b, prev_psum, n_pix, C, K,
+  launch_pdl(film_fold_kernel, dim3(B), dim3(threads), smem, (cudaStream_t)stream, head_w, head_b, film_w, film_b, prev_psum, n_pix, C, K,
                                                              K_prev, gamma_beta, eff_w, eff_b);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;

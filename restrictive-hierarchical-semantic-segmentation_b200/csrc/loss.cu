@@ -17,6 +17,7 @@ template <int K, int VEC, int ITER, int THREADS, bool LOGITS>
 __global__ void __launch_bounds__(THREADS)
 loss_stats_kernel(const float* __restrict__ outs, const float* __restrict__ targets, long t_bstride,
                   long t_cstride, long N, double* __restrict__ stats) {
+  pdl_wait();
   constexpr int NWARP = THREADS / 32;
   constexpr int NS = RHSEG_NSTAT;
   __shared__ float red[NWARP][K * NS];
@@ -156,6 +157,7 @@ __device__ void finalize_level(const double* __restrict__ stats, const float* __
 __global__ void __launch_bounds__(256)
 loss_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ weights, int B, int K,
                      double smooth, float* __restrict__ out4, float* __restrict__ coef) {
+  pdl_wait();
   __shared__ double sh[4][256];
   finalize_level(stats, weights, B, K, smooth, out4, coef, sh);
 }
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(256)
 step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ weights, StepLevels lv, int B,
                      double smooth, double inv_bn, float* __restrict__ out, float* __restrict__ coef,
                      double* __restrict__ summary) {
+  pdl_wait();
   __shared__ double acc[RHSEG_MAX_LEVELS][4];  // ce_sum, dice_sum, n_dice, n_ce
   __shared__ size_t w_off[RHSEG_MAX_LEVELS + 1], k_off[RHSEG_MAX_LEVELS + 1], c_off[RHSEG_MAX_LEVELS + 1], r_off[RHSEG_MAX_LEVELS + 1];
   const int tid = threadIdx.x, nL = lv.n_levels;
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(THREADS)
 loss_bwd_kernel(const float* __restrict__ outs, const float* __restrict__ targets, long t_bstride,
                 long t_cstride, const float* __restrict__ coef, const float* __restrict__ g_ce,
                 const float* __restrict__ g_dice, long N, float* __restrict__ dz) {
+  pdl_wait();
   const int b = blockIdx.y;
   const long px = ((long)blockIdx.x * THREADS + threadIdx.x) * VEC;
   if (px >= N) return;
@@ -386,6 +390,7 @@ template <int K, int VEC, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 consistency_kernel(const float* __restrict__ cur, const float* __restrict__ prev, const int32_t* __restrict__ table,
                    int K_prev, long N, double* __restrict__ sums) {
+  pdl_wait();
   constexpr int NWARP = THREADS / 32;
   __shared__ float red[NWARP][K];
   const int b = blockIdx.y, tid = threadIdx.x;
@@ -453,12 +458,12 @@ extern "C" int rhseg_loss_stats(const float* outs, const float* targets, long t_
   RHSEG_DISPATCH_K(K, {
     if (can_vec4(outs, targets, t_bstride, t_cstride, N)) {
       dim3 grid((unsigned)((N + THREADS * 4 * ITER - 1) / (THREADS * 4 * ITER)), B);
-      if (logits_input) loss_stats_kernel<KK, 4, ITER, THREADS, true><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, N, stats);
-      else loss_stats_kernel<KK, 4, ITER, THREADS, false><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, N, stats);
+      if (logits_input) launch_pdl(loss_stats_kernel<KK, 4, ITER, THREADS, true>, dim3(grid), dim3(THREADS), 0, st, outs, targets, t_bstride, t_cstride, N, stats);
+      else launch_pdl(loss_stats_kernel<KK, 4, ITER, THREADS, false>, dim3(grid), dim3(THREADS), 0, st, outs, targets, t_bstride, t_cstride, N, stats);
     } else {
       dim3 grid((unsigned)((N + THREADS * ITER - 1) / (THREADS * ITER)), B);
-      if (logits_input) loss_stats_kernel<KK, 1, ITER, THREADS, true><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, N, stats);
-      else loss_stats_kernel<KK, 1, ITER, THREADS, false><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, N, stats);
+      if (logits_input) launch_pdl(loss_stats_kernel<KK, 1, ITER, THREADS, true>, dim3(grid), dim3(THREADS), 0, st, outs, targets, t_bstride, t_cstride, N, stats);
+      else launch_pdl(loss_stats_kernel<KK, 1, ITER, THREADS, false>, dim3(grid), dim3(THREADS), 0, st, outs, targets, t_bstride, t_cstride, N, stats);
     }
   });
   RHSEG_LAUNCH_CHECK();
@@ -468,7 +473,7 @@ extern "C" int rhseg_loss_stats(const float* outs, const float* targets, long t_
 extern "C" int rhseg_loss_finalize(const double* stats, const float* weights, int B, int K, double smooth,
                                    float* out4, float* coef, void* stream) {
   if (!stats || !weights || !out4 || !coef || B <= 0 || K <= 0) return RHSEG_ERR_ARG;
-  loss_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(stats, weights, B, K, smooth, out4, coef);
+  launch_pdl(loss_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, stats, weights, B, K, smooth, out4, coef);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }
@@ -484,12 +489,12 @@ extern "C" int rhseg_loss_bwd(const float* outs, const float* targets, long t_bs
   RHSEG_DISPATCH_K(K, {
     if (can_vec4(outs, targets, t_bstride, t_cstride, N) && ((reinterpret_cast<uintptr_t>(dz) & 15u) == 0)) {
       dim3 grid((unsigned)((N / 4 + THREADS - 1) / THREADS), B);
-      if (logits_input) loss_bwd_kernel<KK, 4, THREADS, true><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
-      else loss_bwd_kernel<KK, 4, THREADS, false><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
+      if (logits_input) launch_pdl(loss_bwd_kernel<KK, 4, THREADS, true>, dim3(grid), dim3(THREADS), 0, st, outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
+      else launch_pdl(loss_bwd_kernel<KK, 4, THREADS, false>, dim3(grid), dim3(THREADS), 0, st, outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
     } else {
       dim3 grid((unsigned)((N + THREADS - 1) / THREADS), B);
-      if (logits_input) loss_bwd_kernel<KK, 1, THREADS, true><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
-      else loss_bwd_kernel<KK, 1, THREADS, false><<<grid, THREADS, 0, st>>>(outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
+      if (logits_input) launch_pdl(loss_bwd_kernel<KK, 1, THREADS, true>, dim3(grid), dim3(THREADS), 0, st, outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
+      else launch_pdl(loss_bwd_kernel<KK, 1, THREADS, false>, dim3(grid), dim3(THREADS), 0, st, outs, targets, t_bstride, t_cstride, coef, g_ce, g_dice, N, dz);
     }
   });
   RHSEG_LAUNCH_CHECK();
@@ -508,10 +513,10 @@ extern "C" int rhseg_consistency_sums(const float* cur, const float* prev, const
     if (can_vec4(cur, prev, 0, 0, N)) {
       const long vecs = N / 4;
       dim3 grid((unsigned)min((long)1024, (vecs + THREADS - 1) / THREADS), B);
-      consistency_kernel<KK, 4, THREADS><<<grid, THREADS, 0, st>>>(cur, prev, table, K_prev, N, sums);
+      launch_pdl(consistency_kernel<KK, 4, THREADS>, dim3(grid), dim3(THREADS), 0, st, cur, prev, table, K_prev, N, sums);
     } else {
       dim3 grid((unsigned)min((long)1024, (N + THREADS - 1) / THREADS), B);
-      consistency_kernel<KK, 1, THREADS><<<grid, THREADS, 0, st>>>(cur, prev, table, K_prev, N, sums);
+      launch_pdl(consistency_kernel<KK, 1, THREADS>, dim3(grid), dim3(THREADS), 0, st, cur, prev, table, K_prev, N, sums);
     }
   });
   RHSEG_LAUNCH_CHECK();
@@ -531,7 +536,7 @@ extern "C" int rhseg_step_finalize(const void* eval_words, const float* weights_
     lv.G[L] = L == 0 ? 0 : groups_per_level[L];
     lv.child[L] = L == 0 ? 0 : 1;
   }
-  step_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(eval_words), weights_all, lv, B,
+  launch_pdl(step_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const double*>(eval_words), weights_all, lv, B,
                                                             smooth, 1.0 / ((double)B * (double)n_pix), out, coef_all, summary);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;

@@ -26,6 +26,7 @@ template <int K, int VEC, int ITER, int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS)
 confusion_kernel(const float* __restrict__ probs, long p_bstride, long p_cstride, const float* __restrict__ targets,
                  long t_bstride, long t_cstride, long N, int child, unsigned long long* __restrict__ conf) {
+  pdl_wait();
   constexpr int NCMAX = K + 1;
   __shared__ int hist[NCMAX * NCMAX];
   const int nc = child ? K + 1 : K;
@@ -84,6 +85,7 @@ template <int K, int VEC, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 predict_kernel(const float* __restrict__ logits, const float* __restrict__ targets, long t_bstride, long t_cstride,
                long N, float* __restrict__ onehot, float* __restrict__ eval_t, int32_t* __restrict__ pred_idx) {
+  pdl_wait();
   const int b = blockIdx.y;
   const long px = ((long)blockIdx.x * THREADS + threadIdx.x) * VEC;
   if (px >= N) return;
@@ -123,6 +125,7 @@ predict_kernel(const float* __restrict__ logits, const float* __restrict__ targe
 //   row 0 F1 = 2tp / (2tp + fn + fp)     row 1 Jaccard = tp / (colsum + rowsum - tp)
 //   row 2 Accuracy(average=None) = tp / (tp + fn)   row 3 Precision = tp / (tp + fp)   row 4 Recall
 __global__ void metric_ratios_kernel(const long long* __restrict__ conf, int nc, float* __restrict__ out) {
+  pdl_wait();
   const int c = threadIdx.x;
   if (c >= nc) return;
   long long tp = conf[c * nc + c], row = 0, col = 0;
@@ -155,6 +158,7 @@ level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ ta
                   const unsigned char* __restrict__ prev_idx, const int32_t* __restrict__ table, long N, int child,
                   double* __restrict__ stats, double* __restrict__ cons, unsigned long long* __restrict__ conf,
                   unsigned char* __restrict__ idx_out) {
+  pdl_wait();
   __shared__ float red[THREADS / 32][EvalAccum<K>::NACC];
   __shared__ int hist[(K + 1) * (K + 1)];
   const int b = blockIdx.y, tid = threadIdx.x;
@@ -204,6 +208,7 @@ struct StitchTable {
 template <int VEC, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 stitch_kernel(const float* __restrict__ leaves, int n_leaves, long N, StitchTable tab, float* __restrict__ out) {
+  pdl_wait();
   const int b = blockIdx.y;
   const long px = ((long)blockIdx.x * THREADS + threadIdx.x) * VEC;
   if (px >= N) return;
@@ -250,10 +255,10 @@ static int confusion_launch(const float* probs, long p_bs, long p_cs, const floa
   RHSEG_DISPATCH_K(K, {
     if (v4) {
       dim3 grid((unsigned)((N + THREADS * 4 * ITER - 1) / (THREADS * 4 * ITER)), B);
-      confusion_kernel<KK, 4, ITER, THREADS, MODE><<<grid, THREADS, 0, st>>>(probs, p_bs, p_cs, targets, t_bs, t_cs, N, child, c);
+      launch_pdl(confusion_kernel<KK, 4, ITER, THREADS, MODE>, dim3(grid), dim3(THREADS), 0, st, probs, p_bs, p_cs, targets, t_bs, t_cs, N, child, c);
     } else {
       dim3 grid((unsigned)((N + THREADS * ITER - 1) / (THREADS * ITER)), B);
-      confusion_kernel<KK, 1, ITER, THREADS, MODE><<<grid, THREADS, 0, st>>>(probs, p_bs, p_cs, targets, t_bs, t_cs, N, child, c);
+      launch_pdl(confusion_kernel<KK, 1, ITER, THREADS, MODE>, dim3(grid), dim3(THREADS), 0, st, probs, p_bs, p_cs, targets, t_bs, t_cs, N, child, c);
     }
   });
   RHSEG_LAUNCH_CHECK();
@@ -295,10 +300,10 @@ extern "C" int rhseg_predict_onehot(const float* logits, const float* targets, l
   RHSEG_DISPATCH_K(K, {
     if (v4) {
       dim3 grid((unsigned)((N / 4 + THREADS - 1) / THREADS), B);
-      predict_kernel<KK, 4, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, N, onehot, eval_t, pred_idx);
+      launch_pdl(predict_kernel<KK, 4, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, N, onehot, eval_t, pred_idx);
     } else {
       dim3 grid((unsigned)((N + THREADS - 1) / THREADS), B);
-      predict_kernel<KK, 1, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, N, onehot, eval_t, pred_idx);
+      launch_pdl(predict_kernel<KK, 1, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, N, onehot, eval_t, pred_idx);
     }
   });
   RHSEG_LAUNCH_CHECK();
@@ -307,7 +312,7 @@ extern "C" int rhseg_predict_onehot(const float* logits, const float* targets, l
 
 extern "C" int rhseg_metric_ratios(const int64_t* conf, int nc, float* out5, void* stream) {
   if (!conf || !out5 || nc < 1 || nc > RHSEG_MAX_K + 1) return RHSEG_ERR_ARG;
-  metric_ratios_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(conf), nc, out5);
+  launch_pdl(metric_ratios_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, reinterpret_cast<const long long*>(conf), nc, out5);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }
@@ -339,14 +344,14 @@ extern "C" int rhseg_level_eval(const float* logits, const float* targets, long 
     if (v4) {
       dim3 grid((unsigned)balanced_grid((N + THREADS * 4 - 1) / (THREADS * 4), slots), B);
       if (tune == 1)
-        level_eval_kernel<KK, 4, 3, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
+        launch_pdl(level_eval_kernel<KK, 4, 3, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
             pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
       else
-        level_eval_kernel<KK, 4, 2, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
+        launch_pdl(level_eval_kernel<KK, 4, 2, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
             pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     } else {
       dim3 grid((unsigned)balanced_grid((N + THREADS - 1) / THREADS, slots), B);
-      level_eval_kernel<KK, 1, 2, THREADS><<<grid, THREADS, 0, st>>>(logits, targets, t_bstride, t_cstride, parent_targets,
+      launch_pdl(level_eval_kernel<KK, 1, 2, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
           pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     }
   });
@@ -369,10 +374,10 @@ extern "C" int rhseg_stitch_levels(const float* leaves, int B, int n_leaves, int
   cudaStream_t st = (cudaStream_t)stream;
   if (N % 4 == 0 && aligned16(leaves) && aligned16(out)) {
     dim3 grid((unsigned)((N / 4 + THREADS - 1) / THREADS), B);
-    stitch_kernel<4, THREADS><<<grid, THREADS, 0, st>>>(leaves, n_leaves, N, tab, out);
+    launch_pdl(stitch_kernel<4, THREADS>, dim3(grid), dim3(THREADS), 0, st, leaves, n_leaves, N, tab, out);
   } else {
     dim3 grid((unsigned)((N + THREADS - 1) / THREADS), B);
-    stitch_kernel<1, THREADS><<<grid, THREADS, 0, st>>>(leaves, n_leaves, N, tab, out);
+    launch_pdl(stitch_kernel<1, THREADS>, dim3(grid), dim3(THREADS), 0, st, leaves, n_leaves, N, tab, out);
   }
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
@@ -387,6 +392,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 concat_planes_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, long N,
                      float* __restrict__ out) {
+  pdl_wait();
   const int plane = blockIdx.y;              // (sample, output channel)
   const int c_out = ca + cb;
   const int s = plane / c_out, c = plane - s * c_out;
@@ -404,8 +410,8 @@ extern "C" int rhseg_concat_image_logits(const float* image, int c_image, const 
   const bool v4 = N % 4 == 0 && aligned16(image) && aligned16(logits) && aligned16(out);
   const long per = v4 ? 1024 : 256;
   dim3 grid((unsigned)std::min<long>(64, (N + per - 1) / per), (unsigned)(B * (c_image + K)));
-  if (v4) concat_planes_kernel<4><<<grid, 256, 0, st>>>(image, c_image, logits, K, N, out);
-  else concat_planes_kernel<1><<<grid, 256, 0, st>>>(image, c_image, logits, K, N, out);
+  if (v4) launch_pdl(concat_planes_kernel<4>, dim3(grid), dim3(256), 0, st, image, c_image, logits, K, N, out);
+  else launch_pdl(concat_planes_kernel<1>, dim3(grid), dim3(256), 0, st, image, c_image, logits, K, N, out);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }

@@ -38,6 +38,7 @@ template <int K, int SRC, int MODE>
 __global__ void __launch_bounds__(ADJ_THREADS)
 upsample_adjoint_tiled_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, int H, int W, float sy,
                               float sx, int ry_max, int rx_max, float* __restrict__ dz_lo) {
+  pdl_wait();
   extern __shared__ __align__(16) float sm[];
   float* reg = sm;                                  // [K][ry_max][rx_max]   hi-res gradient of the support region
   float* tmp = sm + (size_t)K * ry_max * rx_max;    // [K][ry_max][ADJ_TW]   after the x reduction
@@ -196,6 +197,7 @@ template <int K, int SRC, int MODE>
 __global__ void __launch_bounds__(XR_THREADS)
 dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, int H, int W, float sx, int XR_ROWS,
                        float* __restrict__ tmpx) {
+  pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int Wp = W + 4;
   float* dzs = sm;                                   // [K][XR_ROWS][Wp]
@@ -327,6 +329,7 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
 // pass 2: dz_lo[b][k][i][j] = sum_y wy(y, i) tmpx[b][k][y][j]
 __global__ void __launch_bounds__(256)
 yreduce_kernel(const float* __restrict__ tmpx, int Hf, int Wf, int H, float sy, long total, float* __restrict__ dz_lo) {
+  pdl_wait();
   const long idx = (long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
   const int j = (int)(idx % Wf);
@@ -347,6 +350,7 @@ yreduce_kernel(const float* __restrict__ tmpx, int Hf, int Wf, int H, float sy, 
 template <int K, int VEC, int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 dz_fullres_fused_kernel(FusedDzArgs fa, long N, float* __restrict__ dz_out) {
+  pdl_wait();
   const int b = blockIdx.y;
   const long px = ((long)blockIdx.x * THREADS + threadIdx.x) * VEC;
   if (px >= N) return;
@@ -449,10 +453,10 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
       if (per_sm < 1) per_sm = 1;
       const long slots = std::max<long>(1, (long)per_sm * device_sm_count() / B);
       dim3 grid(balanced_grid((H + ROWS - 1) / ROWS, slots), B);
-      kern<<<grid, XR_THREADS, smem, st>>>(dz_hi, fa, Wf, H, W, sx, ROWS, tmpx);
+      launch_pdl(kern, dim3(grid), dim3(XR_THREADS), smem, st, dz_hi, fa, Wf, H, W, sx, ROWS, tmpx);
       RHSEG_LAUNCH_CHECK();
       const long total = (long)B * K * Hf * Wf;
-      yreduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tmpx, Hf, Wf, H, sy, total, dz_lo);
+      launch_pdl(yreduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, tmpx, Hf, Wf, H, sy, total, dz_lo);
       RHSEG_LAUNCH_CHECK();
       return RHSEG_OK;
     }
@@ -466,7 +470,7 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
   auto kern = upsample_adjoint_tiled_kernel<K, SRC, MODE>;
   if (smem > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((Wf + ADJ_TW - 1) / ADJ_TW, (Hf + ADJ_TH - 1) / ADJ_TH, B);
-  kern<<<grid, ADJ_THREADS, smem, st>>>(dz_hi, fa, Hf, Wf, H, W, sy, sx, ry_max, rx_max, dz_lo);
+  launch_pdl(kern, dim3(grid), dim3(ADJ_THREADS), smem, st, dz_hi, fa, Hf, Wf, H, W, sy, sx, ry_max, rx_max, dz_lo);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }
@@ -524,14 +528,14 @@ extern "C" int rhseg_head_dz_fullres_fused(const float* logits, const float* tar
   RHSEG_DISPATCH_K(K, {
     if (v4) {
       dim3 grid((unsigned)((N / 4 + THREADS - 1) / THREADS), B);
-      if (act_mode == RHSEG_ACT_SIGMOID) dz_fullres_fused_kernel<KK, 4, RHSEG_ACT_SIGMOID, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
-      else if (act_mode == RHSEG_ACT_GROUPED) dz_fullres_fused_kernel<KK, 4, RHSEG_ACT_GROUPED, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
-      else dz_fullres_fused_kernel<KK, 4, RHSEG_ACT_ZEROS, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
+      if (act_mode == RHSEG_ACT_SIGMOID) launch_pdl(dz_fullres_fused_kernel<KK, 4, RHSEG_ACT_SIGMOID, THREADS>, dim3(grid), dim3(THREADS), 0, st, fa, N, dz_out);
+      else if (act_mode == RHSEG_ACT_GROUPED) launch_pdl(dz_fullres_fused_kernel<KK, 4, RHSEG_ACT_GROUPED, THREADS>, dim3(grid), dim3(THREADS), 0, st, fa, N, dz_out);
+      else launch_pdl(dz_fullres_fused_kernel<KK, 4, RHSEG_ACT_ZEROS, THREADS>, dim3(grid), dim3(THREADS), 0, st, fa, N, dz_out);
     } else {
       dim3 grid((unsigned)((N + THREADS - 1) / THREADS), B);
-      if (act_mode == RHSEG_ACT_SIGMOID) dz_fullres_fused_kernel<KK, 1, RHSEG_ACT_SIGMOID, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
-      else if (act_mode == RHSEG_ACT_GROUPED) dz_fullres_fused_kernel<KK, 1, RHSEG_ACT_GROUPED, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
-      else dz_fullres_fused_kernel<KK, 1, RHSEG_ACT_ZEROS, THREADS><<<grid, THREADS, 0, st>>>(fa, N, dz_out);
+      if (act_mode == RHSEG_ACT_SIGMOID) launch_pdl(dz_fullres_fused_kernel<KK, 1, RHSEG_ACT_SIGMOID, THREADS>, dim3(grid), dim3(THREADS), 0, st, fa, N, dz_out);
+      else if (act_mode == RHSEG_ACT_GROUPED) launch_pdl(dz_fullres_fused_kernel<KK, 1, RHSEG_ACT_GROUPED, THREADS>, dim3(grid), dim3(THREADS), 0, st, fa, N, dz_out);
+      else launch_pdl(dz_fullres_fused_kernel<KK, 1, RHSEG_ACT_ZEROS, THREADS>, dim3(grid), dim3(THREADS), 0, st, fa, N, dz_out);
     }
   });
   RHSEG_LAUNCH_CHECK();
