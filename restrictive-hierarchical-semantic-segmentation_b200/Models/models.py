@@ -44,6 +44,20 @@ def _leaf_count(hierarchy):
 class _HierarchyMixin:
     """Shared construction / forward of the multi-level head for both donors."""
 
+    # SURVEY 8(f4): the reference re-runs the donor on the SAME input once per level (models.py:267, :277,
+    # :757, :773).  In train() mode every pass updates the BatchNorm running statistics and owns its autograd
+    # branch, so all passes are kept.  In eval() mode the passes are bit-identical (frozen statistics, no
+    # dropout), so one pass is run and its feature map feeds every level: same outputs, 1/levels of the donor
+    # cost.  Set to False to replay the reference's pass count exactly.
+    reuse_backbone_in_eval = True
+
+    def _level_features(self, run_backbone, x):
+        n = self._tree.num_levels
+        if not self.training and self.reuse_backbone_in_eval:
+            f = run_backbone(x)
+            return [f] * n
+        return [run_backbone(x) for _ in range(n)]
+
     def _init_hierarchy(self, hierarchy, feat_ch, make_head, head_list_name):
         tree = ClassTree(hierarchy)
         self._tree = tree
@@ -85,7 +99,7 @@ class UNet(nn.Module, _HierarchyMixin):
             return [], self.out_flat(self._run_unet(x))
         # one donor pass per level on the same input, exactly like the reference (:267, :277):
         # every level gets its own feature tensor, autograd branch and BN running-stat update
-        feats = [self._run_unet(x) for _ in range(self._tree.num_levels)]
+        feats = self._level_features(self._run_unet, x)
         return self._head_forward(feats, [h.conv for h in self.heads])
 
 
@@ -123,7 +137,7 @@ class HighResolutionNet(nn.Module, _HierarchyMixin):
         if self.model_type == 0:
             z = self.classifier(self._forward_backbone(x))
             return [], F.interpolate(z, size=size, mode="bilinear", align_corners=self.align_corners)
-        feats = [self._forward_backbone(x) for _ in range(self._tree.num_levels)]
+        feats = self._level_features(self._forward_backbone, x)
         return self._head_forward(feats, list(self.classifiers), out_size=size)
 
     def init_weights(self, pretrained="", device="cpu"):

@@ -135,6 +135,9 @@ struct EvalAccum {
       if constexpr (VEC == 4) {
         const uchar4 q = *reinterpret_cast<const uchar4*>(prev_idx + (size_t)b * N + px);
         pidx[0] = q.x; pidx[1] = q.y; pidx[2] = q.z; pidx[3] = q.w;
+      } else if constexpr (VEC == 2) {
+        const uchar2 q = *reinterpret_cast<const uchar2*>(prev_idx + (size_t)b * N + px);
+        pidx[0] = q.x; pidx[1] = q.y;
       } else {
         pidx[0] = prev_idx[(size_t)b * N + px];
       }
@@ -147,6 +150,8 @@ struct EvalAccum {
     if (ok && idx_out) {
       if constexpr (VEC == 4) {
         *reinterpret_cast<uchar4*>(idx_out + (size_t)b * N + px) = make_uchar4(my_idx[0], my_idx[1], my_idx[2], my_idx[3]);
+      } else if constexpr (VEC == 2) {
+        *reinterpret_cast<uchar2*>(idx_out + (size_t)b * N + px) = make_uchar2(my_idx[0], my_idx[1]);
       } else {
         idx_out[(size_t)b * N + px] = my_idx[0];
       }

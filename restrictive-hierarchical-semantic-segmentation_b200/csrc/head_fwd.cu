@@ -488,7 +488,7 @@ struct EvalArgs {
 };
 
 template <int K, int VEC, int MODE, bool EVAL>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, VEC == 2 ? 3 : 2)
 upsample_act_tiled_kernel(const float* __restrict__ z_lo, const float* __restrict__ prev_probs,
                           const int32_t* __restrict__ table, int Hf, int Wf, int H, int W, int K_prev, float sy,
                           float sx, int tiles_x, int tiles_per_sample, float* __restrict__ logits,
@@ -669,6 +669,17 @@ static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32
     if (ea) v4 = v4 && al16(ea->targets) && ea->t_bstride % 4 == 0 && ea->t_cstride % 4 == 0 && al4(ea->prev_idx) && al4(ea->idx_out) &&
                  (!ea->parent_targets || (al16(ea->parent_targets) && ea->pt_bstride % 4 == 0 && ea->pt_cstride % 4 == 0));
     const EvalArgs none{};
+    static int tune = -1;
+    if (tune < 0) { const char* e = getenv("RHSEG_TUNE_UPACT"); tune = e ? atoi(e) : 0; }
+    if (tune == 1 && v4) {  // 2 pixels per thread: fewer live registers, more resident warps
+      const int slots2 = std::max(1, device_sm_count() * 3 / B);
+      const int tiles_x = (W + 31) / 32, tiles = tiles_x * ((H + 15) / 16);
+      dim3 grid(balanced_grid(tiles, slots2), B);
+      if (ea) launch_pdl(upsample_act_tiled_kernel<K, 2, MODE, true>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
+      else launch_pdl(upsample_act_tiled_kernel<K, 2, MODE, false>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
+      RHSEG_LAUNCH_CHECK();
+      return RHSEG_OK;
+    }
     const int slots = std::max(1, device_sm_count() * 2 / B);  // CTAs per sample: one resident wave at 2 CTAs/SM
     if (v4) {
       const int tiles_x = (W + 63) / 64, tiles = tiles_x * ((H + 15) / 16);

@@ -317,3 +317,38 @@ def test_flat_seven_class_losses_and_metrics_match_reference():
     want = O.level_metrics(ref_oh[0], ref_et[0], 7, False)
     for key, mod in (("iou", pm.Jaccardindex()), ("dice", pm.DiceScore()), ("recall", pm.Recall())):
         assert torch.equal(mod(onehot, eval_t, DEV, 7, False).cpu(), want[key])
+
+
+def test_eval_mode_backbone_reuse_is_output_identical():
+    """SURVEY 8(f4): in eval() the per-level donor passes are identical, so one pass feeds all levels;
+    outputs equal the pass-per-level replay bit for bit, and train() mode still runs one pass per level."""
+    from rhseg_b200.Models import models
+    fx = Fixture("unet_ext")
+    torch.manual_seed(9)
+    m = models.UNet(size=32, n_channels=3, hierarchy=fx.tree, model_type=1).to(DEV)
+    x = torch.randn(2, 3, 32, 48, device=DEV)
+    calls = {"n": 0}
+    orig = m._run_unet
+
+    def counted(inp):
+        calls["n"] += 1
+        return orig(inp)
+
+    m._run_unet = counted
+    m.eval()
+    with torch.no_grad():
+        p1, z1 = m(x, type=1, hierarchy=fx.tree)
+        assert calls["n"] == 1
+        m.reuse_backbone_in_eval = False
+        p2, z2 = m(x, type=1, hierarchy=fx.tree)
+        assert calls["n"] == 1 + len(m.levels)
+    for a, b in zip(p1 + z1, p2 + z2):
+        assert torch.equal(a, b)
+    m.reuse_backbone_in_eval = True
+    m.train()
+    calls["n"] = 0
+    p3, z3 = m(x, type=1, hierarchy=fx.tree)
+    assert calls["n"] == len(m.levels)
+    sum(z.sum() for z in z3).backward()
+    assert m.heads[0].conv.weight.grad is not None and m.films[0].mlp[1].weight.grad is not None
+    assert m.inc0.conv.conv[0].weight.grad is not None
