@@ -113,6 +113,8 @@ class GpuStep:
         self.out_size = None if wl["scale"] == 1 else (wl["H"], wl["W"])
         self.ce, self.dice = losses.CrossEntropyLoss(), losses.SoftDiceLoss()
         self.fused = rhseg_b200.FusedHierStep(self.tree, data["weights"])
+        # room behind the step summary for the head / FiLM parameter gradients (the data-parallel exchange buffer)
+        self.fused.exchange_tail = sum(p.numel() for grp in self.params for p in grp)
         self.result = None
 
     def targets(self):
@@ -129,7 +131,7 @@ class GpuStep:
         leaves = self.feats + [p for grp in self.params for p in grp]
         self.grads = torch.autograd.grad(out.loss, leaves)  # dfeats per level + head / FiLM parameter grads
         self.result = (out.scalars, out.ratios)
-        self.confusion, self.summary = out.confusion, out.summary
+        self.confusion, self.summary, self.exchange = out.confusion, out.summary, out.exchange
         return self.result
 
     def step_dropin(self):
@@ -250,15 +252,30 @@ def run_ours(args, rank, world, local_rank):
 
     from rhseg_b200 import dist as rdist
 
+    peer = {"px": None, "kind": "none" if world == 1 else "nccl"}
+
     def exchange(result):
         """The path's only cross-rank step: ONE all-reduce of the packed step summary (loss terms,
         valid-sample counts, confusion matrices; rhseg_b200.dist) + the head/FiLM parameter gradients
-        (a few thousand floats).  Pixel data never leaves its GPU."""
+        (a few thousand floats).  Pixel data never leaves its GPU.  Single node: one kernel over NVLink
+        peer memory (rhseg_xchg_all_reduce); RHSEG_EXCHANGE=nccl (or no P2P) -> rhseg_pack_f64 + NCCL."""
         if world == 1:
             return
-        buf = torch.cat([st.summary] + [g.reshape(-1).double() for g in st.grads[len(st.feats):]])
+        grads = st.grads[len(st.feats):]
+        if peer["px"] is not None:
+            st.global_summary = peer["px"].all_reduce(st.summary, grads, out=st.exchange)
+            return
+        buf = rdist.pack_exchange(st.summary, grads, out=st.exchange)  # one rhseg_pack_f64 launch
         torch.distributed.all_reduce(buf)
         st.global_summary = buf
+
+    if world > 1 and os.environ.get("RHSEG_EXCHANGE", "p2p") == "p2p":
+        st.step()  # sizes the exchange buffer
+        try:
+            peer["px"] = rdist.PeerExchange(st.exchange.numel())
+            peer["kind"] = "p2p"
+        except Exception as e:
+            sys.stderr.write("peer-memory exchange unavailable (%r); using NCCL\n" % (e,))
 
     # ---- device-resident timing (`value`) ----
     for _ in range(max(args.warmup, 3)):
@@ -409,7 +426,7 @@ def run_ours(args, rank, world, local_rank):
                    "batch_per_gpu": B, "image": [wl["H"], wl["W"]], "feat_hw": list(feat_hw(wl)),
                    "step": "head fwd + train-path prediction + 5 confusion metrics + CE/Dice/consistency + bwd (dfeats, head+FiLM grads); fused step API",
                    "l2_policy": "inputs larger than L2 (%.0f MB of features per step vs 126 MB L2)" % (sum(f.numel() * 4 for f in st.feats) / 1e6),
-                   "cuda_graph": graph is not None, "collective": "1 all-reduce/step (loss+metrics+head grads)" if world > 1 else "none"},
+                   "cuda_graph": graph is not None, "collective": ("1 all-reduce/step (loss+metrics+head grads), %s" % {"p2p": "one peer-memory kernel over NVLink (rhseg_xchg_all_reduce)", "nccl": "rhseg_pack_f64 + NCCL"}[peer["kind"]]) if world > 1 else "none"},
         "step_bytes": {"algorithmic_head_loss_fwd_bwd": alg["step"], "metrics": alg["metrics"],
                        "frac_of_hbm_peak_whole_step": (alg["step"] + alg["metrics"]) / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
         "roofline": {"kernel": "conv_bwd_kernel (1x1-conv backward, level %d)" % dom, "bound": "hbm", "achieved": achieved,

@@ -289,6 +289,40 @@ int rhseg_stitch_levels(const float* leaves, int B, int n_leaves, int n_pix, con
 int rhseg_concat_image_logits(const float* image, int c_image, const float* logits, int K, int B, int n_pix,
                               float* out, void* stream);
 
+/* Data-parallel exchange buffer (no reference counterpart: train.py:201-241 is single-process; the
+ * batch shards over ranks and ONE all-reduce of a packed fp64 buffer carries the step summary and
+ * the head / FiLM parameter gradients).
+ * rhseg_pack_f64:   out[off_k + i] = (double) srcs[k][i]   for n <= 32 fp32 device tensors of
+ *                   counts[k] elements, back to back in list order (one launch).
+ * rhseg_unpack_f32: dsts[k][i] = (float)(in[off_k + i] * scale)   the inverse, with the averaging
+ *                   factor folded in.  srcs / dsts / counts are HOST arrays (of device pointers).   */
+int rhseg_pack_f64(const void* const* srcs, const long* counts, int n, double* out, void* stream);
+int rhseg_unpack_f32(const double* in, double scale, void* const* dsts, const long* counts, int n, void* stream);
+
+/* One-shot all-reduce (SUM) of the exchange buffer over NVLink peer memory: single node, one process
+ * per GPU, replaces the NCCL all-reduce of the ~100 KB buffer (pure latency) by ONE kernel: it converts
+ * the rank's contribution to fp64, pushes every element into each peer's receive area as a
+ * self-validating 16-byte record {lo32, epoch, hi32, epoch}, polls its own memory for the peers'
+ * records and adds them in rank order (bit-identical results on every rank; one NVLink one-way
+ * latency; no fences, flags or barriers).  CUDA-graph capturable (the epoch lives in device memory).
+ *   rhseg_xchg_create : allocates this rank's receive area (2 * world * capacity * 16 bytes) and returns
+ *                       its CUDA IPC handle (RHSEG_XCHG_HANDLE_BYTES bytes) for the peers.
+ *   rhseg_xchg_connect: maps the peers' areas; handles = world * RHSEG_XCHG_HANDLE_BYTES bytes in rank
+ *                       order (gathered by the host, e.g. torch.distributed.all_gather).
+ *   rhseg_xchg_all_reduce: out[0..n_sum) = sum_r summary_r ; out[n_sum + off_k + i] = sum_r (double)
+ *                       srcs_r[k][i]  (srcs / counts as in rhseg_pack_f64; out may alias summary;
+ *                       n_sum + sum counts <= capacity).  Every rank calls it with the same sizes, in
+ *                       the same order.
+ *   rhseg_xchg_status : 0, or 1 when a wait for a peer timed out (~2 s; the result is then invalid).
+ * World size <= 16.                                                                               */
+#define RHSEG_XCHG_HANDLE_BYTES 64
+int rhseg_xchg_create(long capacity, int world, void** ctx_out, unsigned char* handle_out);
+int rhseg_xchg_connect(void* ctx, int rank, const unsigned char* handles);
+int rhseg_xchg_all_reduce(void* ctx, const double* summary, long n_sum, const void* const* srcs,
+                          const long* counts, int n, double* out, void* stream);
+int rhseg_xchg_status(void* ctx, int* status_out);
+int rhseg_xchg_destroy(void* ctx);
+
 #ifdef __cplusplus
 }
 #endif

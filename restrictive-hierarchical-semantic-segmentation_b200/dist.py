@@ -63,12 +63,128 @@ def all_reduce_step_summary(scalars, batch_local, confusion, group=None):
     return unpack_global(buf, n, [tuple(c.shape) for c in confusion])
 
 
+def pack_exchange(summary: torch.Tensor, extra: Sequence[torch.Tensor] = (), out: torch.Tensor = None) -> torch.Tensor:
+    """The step's exchange buffer [summary | extra tensors] in fp64.  CUDA: the fp32 `extra` tensors are
+    written behind the summary by ONE kernel (rhseg_pack_f64); with `out` = StepOutput.exchange (allocated by a
+    FusedHierStep whose exchange_tail covers the extras) the summary is already in place and nothing is copied.
+    CPU tensors (gloo tests of the host logic) are concatenated with torch."""
+    if not summary.is_cuda:
+        flat = [summary] + [e.reshape(-1).double() for e in extra]
+        return torch.cat(flat) if len(flat) > 1 else summary.clone()
+    import ctypes
+    from . import native
+    extra = [e if (e.dtype == torch.float32 and e.is_contiguous()) else e.float().contiguous() for e in extra]
+    n_sum = summary.numel()
+    need = n_sum + sum(e.numel() for e in extra)
+    if out is not None and out.data_ptr() == summary.data_ptr() and out.numel() >= need and out.dtype == torch.float64:
+        buf = out[:need]
+    else:
+        buf = torch.empty(need, dtype=torch.float64, device=summary.device)
+        buf[:n_sum].copy_(summary)
+    if extra:
+        ptrs = (ctypes.c_void_p * len(extra))(*[e.data_ptr() for e in extra])
+        cnts = (ctypes.c_long * len(extra))(*[e.numel() for e in extra])
+        native.call("rhseg_pack_f64", ptrs, cnts, len(extra), buf.data_ptr() + 8 * n_sum, native.stream_of(summary))
+    return buf
+
+
+def unpack_exchange(buf: torch.Tensor, n_summary: int, targets: Sequence[torch.Tensor], scale: float = 1.0) -> None:
+    """Inverse of pack_exchange for the gradient part after the all-reduce: targets[k] <- scale * buf slice
+    (fp32, in place; scale = 1/world gives DDP's average).  CUDA: one rhseg_unpack_f32 launch."""
+    if not buf.is_cuda:
+        off = n_summary
+        for t in targets:
+            t.copy_((buf[off:off + t.numel()] * scale).view(t.shape).to(t.dtype))
+            off += t.numel()
+        return
+    import ctypes
+    from . import native
+    for t in targets:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise native.NativeError("unpack_exchange writes contiguous float32 tensors in place")
+    if targets:
+        ptrs = (ctypes.c_void_p * len(targets))(*[t.data_ptr() for t in targets])
+        cnts = (ctypes.c_long * len(targets))(*[t.numel() for t in targets])
+        native.call("rhseg_unpack_f32", buf.data_ptr() + 8 * n_summary, float(scale), ptrs, cnts, len(targets),
+                    native.stream_of(buf))
+
+
+class PeerExchange:
+    """One-shot all-reduce of the exchange buffer over NVLink peer memory (rhseg_xchg_*): single node, one
+    process per GPU.  Construct it once, collectively, after init_process_group (every rank of `group`):
+
+        px = PeerExchange(capacity=out.exchange.numel())
+        buf = px.all_reduce(out.summary, param_grads, out=out.exchange)     # one kernel, graph-capturable
+
+    Raises NativeError when peer mapping is impossible (no P2P between the GPUs); callers then keep the
+    NCCL all-reduce of pack_exchange().  Multi-node jobs use NCCL."""
+
+    def __init__(self, capacity: int, group=None):
+        import ctypes
+        from . import native
+        if not (dist.is_available() and dist.is_initialized()):
+            raise native.NativeError("PeerExchange needs an initialised torch.distributed process group")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.capacity = int(capacity)
+        self._ctx = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * native.XCHG_HANDLE_BYTES)()
+        native.check(native.lib().rhseg_xchg_create(self.capacity, self.world, ctypes.byref(self._ctx), handle), "rhseg_xchg_create")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=group)
+        blob = bytes(torch.cat(gathered).cpu().tolist())
+        # every rank must succeed before anybody uses the buffers
+        rc = native.lib().rhseg_xchg_connect(self._ctx, self.rank, blob)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) != 1:
+            native.lib().rhseg_xchg_destroy(self._ctx)
+            self._ctx = None
+            raise native.NativeError("rhseg_xchg_connect failed on at least one rank (local status %d: %s)"
+                                     % (rc, native.status_string(rc)))
+
+    def all_reduce(self, summary: torch.Tensor, extra: Sequence[torch.Tensor] = (), out: torch.Tensor = None) -> torch.Tensor:
+        """SUM over ranks of [summary | extra...] (fp64), written to `out` (default: a new tensor; `out` may be the
+        StepOutput.exchange buffer whose prefix is `summary`)."""
+        import ctypes
+        from . import native
+        native.require_cuda(summary, *extra)
+        if summary.dtype != torch.float64 or not summary.is_contiguous():
+            raise native.NativeError("the step summary is a contiguous float64 tensor")
+        extra = [e if (e.dtype == torch.float32 and e.is_contiguous()) else e.float().contiguous() for e in extra]
+        need = summary.numel() + sum(e.numel() for e in extra)
+        if need > self.capacity:
+            raise native.NativeError("exchange of %d elements exceeds the PeerExchange capacity %d" % (need, self.capacity))
+        if out is None or out.numel() < need or out.dtype != torch.float64:
+            out = torch.empty(need, dtype=torch.float64, device=summary.device)
+        ptrs = (ctypes.c_void_p * max(1, len(extra)))(*[e.data_ptr() for e in extra])
+        cnts = (ctypes.c_long * max(1, len(extra)))(*[e.numel() for e in extra])
+        native.call("rhseg_xchg_all_reduce", self._ctx, summary.data_ptr(), summary.numel(), ptrs, cnts, len(extra),
+                    out.data_ptr(), native.stream_of(summary))
+        return out[:need]
+
+    def status(self) -> int:
+        """0, or 1 when a wait for a peer timed out (synchronises the device)."""
+        import ctypes
+        from . import native
+        s = ctypes.c_int(0)
+        native.check(native.lib().rhseg_xchg_status(self._ctx, ctypes.byref(s)), "rhseg_xchg_status")
+        return int(s.value)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            from . import native
+            torch.cuda.synchronize()
+            native.lib().rhseg_xchg_destroy(self._ctx)
+            self._ctx = None
+
+
 def all_reduce_summary(summary: torch.Tensor, n_levels: int, conf_shapes, extra: Sequence[torch.Tensor] = (), group=None):
     """Fused-step variant: `summary` is StepOutput.summary (already in the packed layout, written by
     rhseg_step_finalize).  `extra` tensors (e.g. the head / FiLM parameter gradients) ride in the same
     all-reduce.  Returns (global summary dict, reduced extras as fp64 views)."""
-    flat = [summary] + [e.reshape(-1).double() for e in extra]
-    buf = torch.cat(flat) if len(flat) > 1 else summary.clone()
+    buf = pack_exchange(summary, extra)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     out = unpack_global(buf, n_levels, conf_shapes)

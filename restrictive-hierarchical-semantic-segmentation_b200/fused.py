@@ -30,10 +30,11 @@ _I32 = ctypes.c_int32
 class StepOutput:
     """Everything one training step reports, still on the device (no host sync)."""
     __slots__ = ("loss", "scalars", "level_ce", "level_dice", "consistency", "confusion", "ratios", "probs", "logits",
-                 "summary")
+                 "summary", "exchange")
 
-    def __init__(self, loss, scalars, confusion, ratios, probs, logits, n, summary=None):
+    def __init__(self, loss, scalars, confusion, ratios, probs, logits, n, summary=None, exchange=None):
         self.summary = summary                 # fp64 additive per-rank summary for dist.all_reduce_summary
+        self.exchange = exchange               # summary + `exchange_tail` free fp64 slots behind it (dist.pack_exchange)
         self.loss = loss                       # 0-dim, differentiable
         self.scalars = scalars                 # [2 + 4*n] fp32: total, consistency, then (ce, dice, n_dice, n_ce) per level
         self.consistency = scalars[1]
@@ -56,7 +57,7 @@ def _eval_layout(tree: ClassTree, B: int):
 
 class _FusedStepFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tree: ClassTree, out_size, weights_all, smooth, target, *tensors):
+    def forward(ctx, tree: ClassTree, out_size, weights_all, smooth, xchg_tail, target, *tensors):
         n = tree.num_levels
         native.require_cuda(target)
         if target.dtype != torch.float32:
@@ -94,7 +95,8 @@ class _FusedStepFn(torch.autograd.Function):
         scal_all = torch.empty((2 + 4 * n + n_ratio,), dtype=torch.float32, device=dev)
         scalars = scal_all[:2 + 4 * n]
         coef_all = torch.empty((B * sum(tree.head_channels) * 3,), dtype=torch.float32, device=dev)
-        summary = torch.empty((2 + 4 * n + sum(o[3] * o[3] for o in offs),), dtype=torch.float64, device=dev)
+        # [summary | xchg_tail slots for the parameter gradients]: the data-parallel exchange buffer
+        summary = torch.empty((2 + 4 * n + sum(o[3] * o[3] for o in offs) + int(xchg_tail),), dtype=torch.float64, device=dev)
         Ks = (_I32 * n)(*tree.head_channels)
         Gs = (_I32 * n)(*[tree.group_count(L) for L in range(n)])
         call("rhseg_step_finalize", ptr(ws), ptr(weights_all), B, n, Ks, Gs, float(smooth), n_pix, ptr(scal_all),
@@ -129,7 +131,7 @@ class _FusedStepFn(torch.autograd.Function):
         t_bs, t_cs, ch_off, esz = ctx.t_meta
         n_grads = 5 * n - 2
         if g_total is None:
-            return (None,) * (5 + n_grads)
+            return (None,) * (6 + n_grads)
         dev = feats[0].device
         st = stream_of(feats[0])
         tables = tree.device_tables(dev)
@@ -173,11 +175,11 @@ class _FusedStepFn(torch.autograd.Function):
             S, s = sums[L]
             d_feats[L], d_hw[L], d_hb[L], fw_g, fb_g, g_prev = level_weight_backward(
                 tree, L, ctx.dims, feats[L], dz, eff_ws[L], head_w[L], film_w[L - 1] if L > 0 else None, gbs[L],
-                psums[L - 1] if L > 0 else None, S, s, ctx.needs_input_grad[5 + L], st)
+                psums[L - 1] if L > 0 else None, S, s, ctx.needs_input_grad[6 + L], st)
             if L > 0:
                 d_fw[L - 1], d_fb[L - 1] = fw_g, fb_g
             g_uniform, dp_pix, pix_mask = g_prev, dp_prev, prev_mask
-        return (None,) * 5 + tuple(d_feats) + tuple(d_hw) + tuple(d_hb) + tuple(d_fw) + tuple(d_fb)
+        return (None,) * 6 + tuple(d_feats) + tuple(d_hw) + tuple(d_hb) + tuple(d_fw) + tuple(d_fb)
 
 
 class FusedHierStep:
@@ -200,6 +202,9 @@ class FusedHierStep:
         self._weights_host = [float(x) for w in level_weights for x in w]
         self._weights = {}
         self.smooth = float(smooth)
+        # free fp64 slots allocated behind StepOutput.summary (data-parallel jobs: set it to the number of
+        # parameter-gradient elements that ride in the step's all-reduce, see dist.pack_exchange)
+        self.exchange_tail = 0
         if self.tree.num_levels > 8:
             raise native.NativeError("fused step supports trees up to 8 levels deep")
 
@@ -213,7 +218,9 @@ class FusedHierStep:
         n = self.tree.num_levels
         if not (len(feats) == len(head_w) == len(head_b) == n and len(film_w) == len(film_b) == n - 1):
             raise native.NativeError("expected %d levels of features/heads and %d FiLMs" % (n, n - 1))
-        outs = _FusedStepFn.apply(self.tree, out_size, self.weights(feats[0].device), self.smooth, target,
-                                  *feats, *head_w, *head_b, *film_w, *film_b)
+        outs = _FusedStepFn.apply(self.tree, out_size, self.weights(feats[0].device), self.smooth, self.exchange_tail,
+                                  target, *feats, *head_w, *head_b, *film_w, *film_b)
+        xbuf = outs[2 + 4 * n]
         return StepOutput(outs[0], outs[1], list(outs[2:2 + n]), list(outs[2 + n:2 + 2 * n]),
-                          list(outs[2 + 2 * n:2 + 3 * n]), list(outs[2 + 3 * n:2 + 4 * n]), n, outs[2 + 4 * n])
+                          list(outs[2 + 2 * n:2 + 3 * n]), list(outs[2 + 3 * n:2 + 4 * n]), n,
+                          xbuf[:xbuf.numel() - self.exchange_tail], xbuf)

@@ -15,6 +15,7 @@ MAX_K = 16
 KERNEL_MAX_K = 8
 TABLE_INTS = 4 + 5 * MAX_K
 NSTAT = 5
+XCHG_HANDLE_BYTES = 64
 ACT_SIGMOID, ACT_GROUPED, ACT_ZEROS = 0, 1, 2
 
 _c = ctypes
@@ -33,6 +34,13 @@ SIGNATURES = {
     "rhseg_head_act_bwd": [_P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "rhseg_upsample_adjoint": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "rhseg_head_dz_lowres_fused": [_P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "rhseg_pack_f64": [_P, _P, _I, _P, _P],
+    "rhseg_unpack_f32": [_P, _D, _P, _P, _I, _P],
+    "rhseg_xchg_create": [_L, _I, _P, _P],
+    "rhseg_xchg_connect": [_P, _I, _P],
+    "rhseg_xchg_all_reduce": [_P, _P, _L, _P, _P, _I, _P, _P],
+    "rhseg_xchg_status": [_P, _P],
+    "rhseg_xchg_destroy": [_P],
     "rhseg_head_conv_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "rhseg_head_param_grads": [_P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "rhseg_loss_stats": [_P, _P, _L, _L, _I, _I, _I, _I, _P, _P],
@@ -86,6 +94,11 @@ def check(rc, what):
     if rc != 0:
         msg = lib().rhseg_status_string(rc)
         raise NativeError("%s failed: %s (status %d)" % (what, msg.decode() if msg else "?", rc))
+
+
+def status_string(rc) -> str:
+    msg = lib().rhseg_status_string(int(rc))
+    return msg.decode() if msg else "?"
 
 
 def ptr(t):

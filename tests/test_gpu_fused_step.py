@@ -139,3 +139,41 @@ def test_fused_step_summary_matches_pack_layout():
     assert abs(float(glob["total"]) - out.loss.item()) < 1e-5
     assert torch.equal(glob["confusion"][1], out.confusion[1])
     close(extras[0], out.scalars, rtol=1e-6, what="extra")
+
+
+def test_exchange_buffer_pack_and_unpack():
+    """Data-parallel exchange buffer: StepOutput.exchange = [summary | tail]; rhseg_pack_f64 writes the parameter
+    gradients behind the summary in one launch (== torch.cat of the fp64 casts), rhseg_unpack_f32 scales them back."""
+    import rhseg_b200
+    from rhseg_b200 import dist as rdist
+    fx = Fixture("hrnet_tl")
+    step = rhseg_b200.FusedHierStep(fx.tree, fx.level_weights)
+    mk = lambda ts: [t.to(DEV).requires_grad_(True) for t in ts]
+    feats = mk(fx.per_level("feats"))
+    params = [mk(fx.per_level("head_w")), mk(fx.per_level("head_b")), mk(fx.per_level("film_w", n=fx.nL - 1)),
+              mk(fx.per_level("film_b", n=fx.nL - 1))]
+    flat = [p for grp in params for p in grp]
+    step.exchange_tail = sum(p.numel() for p in flat)
+    target = torch.cat(fx.per_level("target"), dim=1).to(DEV)
+    out = step(feats, *params, target, fx.out_size)
+    grads = torch.autograd.grad(out.loss, flat)
+    assert out.exchange.data_ptr() == out.summary.data_ptr()
+    assert out.exchange.numel() == out.summary.numel() + step.exchange_tail
+    want = torch.cat([out.summary] + [g.reshape(-1).double() for g in grads])
+    buf = rdist.pack_exchange(out.summary, grads, out=out.exchange)
+    assert buf.data_ptr() == out.exchange.data_ptr()          # packed in place, the summary was not copied
+    assert torch.equal(buf, want)
+    assert torch.equal(rdist.pack_exchange(out.summary, grads), want)   # without the preallocated tail
+    # a non-contiguous / empty part and a lone summary
+    odd = [grads[0].transpose(0, 1), torch.empty(0, device=DEV), grads[1]]
+    assert torch.equal(rdist.pack_exchange(out.summary, odd),
+                       torch.cat([out.summary] + [g.reshape(-1).double() for g in odd]))
+    assert torch.equal(rdist.pack_exchange(out.summary), out.summary)
+    back = [torch.full_like(g, float("nan")) for g in grads]
+    rdist.unpack_exchange(buf, out.summary.numel(), back, scale=0.25)
+    for b, g in zip(back, grads):
+        assert torch.equal(b, (g.double() * 0.25).float())
+    # results with a tail are the results without one
+    step.exchange_tail = 0
+    out0 = step(feats, *params, target, fx.out_size)
+    assert torch.equal(out0.summary, out.summary) and out0.exchange.numel() == out0.summary.numel()
