@@ -116,6 +116,7 @@ class GpuStep:
         # room behind the step summary for the head / FiLM parameter gradients (the data-parallel exchange buffer)
         self.fused.exchange_tail = sum(p.numel() for grp in self.params for p in grp)
         self.result = None
+        self.one = torch.ones((), device=device)  # d(loss)/d(loss), allocated once instead of a fill per step
 
     def targets(self):
         out, s = [], 0
@@ -129,7 +130,7 @@ class GpuStep:
         hw, hb, fw, fb = self.params
         out = self.fused(self.feats, hw, hb, fw, fb, self.target, self.out_size)
         leaves = self.feats + [p for grp in self.params for p in grp]
-        self.grads = torch.autograd.grad(out.loss, leaves)  # dfeats per level + head / FiLM parameter grads
+        self.grads = torch.autograd.grad(out.loss, leaves, grad_outputs=self.one)  # dfeats per level + head / FiLM parameter grads
         self.result = (out.scalars, out.ratios)
         self.confusion, self.summary, self.exchange = out.confusion, out.summary, out.exchange
         return self.result

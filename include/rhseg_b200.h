@@ -138,22 +138,28 @@ int rhseg_head_act_bwd(const float* logits, const float* prev_probs, const int32
                        float* dz_out, float* dp_prev, void* stream);
 
 /* Adjoint of the bilinear align_corners=True upsample: dz_hi [B,K,H,W] -> dz_lo [B,K,Hf,Wf]
- * (deterministic, separable).  tmp: optional workspace [B,K,H,Wf] fp32; with it (and W % 4 == 0)
- * the halo-free row kernel is used, otherwise the shared-memory tiled kernel.              */
+ * (deterministic, separable).  Three kernels, fastest first:
+ *   flags & RHSEG_DZ_PREZEROED (caller zeroed dz_lo), W % 4 == 0, upsampling: ONE band kernel, each CTA
+ *     reduces a band of hi-res rows along x and y in shared memory and adds its few low-res rows into
+ *     dz_lo (at most two CTAs feed a row, so the fp32 result does not depend on their order);
+ *   tmp != NULL (workspace [B,K,H,Wf] fp32), W % 4 == 0: halo-free row kernel + y-reduction kernel;
+ *   otherwise the shared-memory tiled kernel.                                               */
+#define RHSEG_DZ_PREZEROED 1
 int rhseg_upsample_adjoint(const float* dz_hi, int B, int K, int Hf, int Wf, int H, int W,
-                           float* dz_lo, float* tmp, void* stream);
+                           float* dz_lo, float* tmp, int flags, void* stream);
 
 /* Fused hi-res backward for upsampled heads (HRNet): forms per hi-res pixel
  *   dz_hi = d(g_ce*CE + g_dice*Dice)/dz  (closed form from logits, targets, coef of
  *           rhseg_loss_finalize)  +  activation backward of rhseg_head_act_bwd (g_uniform, dp_pix)
  * and applies the upsample adjoint in the same kernel, so dz_hi is never materialised.
- * Result dz_lo [B,K,Hf,Wf]; dp_prev (+=) as in rhseg_head_act_bwd.                         */
+ * Result dz_lo [B,K,Hf,Wf]; dp_prev (+=) as in rhseg_head_act_bwd.  tmp / flags as in
+ * rhseg_upsample_adjoint.                                                                  */
 int rhseg_head_dz_lowres_fused(const float* logits, const float* targets, long t_bstride, long t_cstride,
                                const float* coef, const float* g_ce, const float* g_dice,
                                const float* prev_probs, const int32_t* table, const double* g_uniform,
                                double inv_npix, const float* dp_pix, uint32_t pix_mask,
                                int B, int K, int K_prev, int Hf, int Wf, int H, int W, int act_mode,
-                               float* dz_lo, float* dp_prev, float* tmp, void* stream);
+                               float* dz_lo, float* dp_prev, float* tmp, int flags, void* stream);
 
 /* 1x1 conv backward at feature resolution: dfeats[b,c,n] = sum_k eff_w[b,k,c] dz[b,k,n];
  * S[b,k,c] = sum_n dz[b,k,n] feats[b,c,n]; s[b,k] = sum_n dz[b,k,n]  (fp64, accumulated with

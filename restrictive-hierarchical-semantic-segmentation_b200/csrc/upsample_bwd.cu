@@ -193,10 +193,15 @@ upsample_adjoint_tiled_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, i
 // ------------------------------------------------------------------------------------
 constexpr int XR_MAXROWS = 8, XR_THREADS = 256, XR_MAXW = 12;
 
-template <int K, int SRC, int MODE>
+// BAND: the CTA owns `band` consecutive hi-res rows; each x-reduced row is scattered straight into a
+// shared-memory accumulator of the few low-res rows the band touches (adjoint of the y interpolation: row y
+// feeds rows i0(y), i1(y) with the forward's own lerp weights) and the accumulator is added into a
+// PRE-ZEROED dz_lo at the end.  band >= taps per low-res row, so a low-res row receives from at most two
+// CTAs and the two-term fp32 sum is order independent: deterministic, no tmpx tensor, no second kernel.
+template <int K, int SRC, int MODE, bool BAND = false>
 __global__ void __launch_bounds__(XR_THREADS)
 dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, int H, int W, float sx, int XR_ROWS,
-                       float* __restrict__ tmpx) {
+                       float* __restrict__ tmpx, int Hf, float sy, int band, int acc_rows, float* __restrict__ dz_lo) {
   pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int Wp = W + 4;
@@ -204,8 +209,14 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
   float* wtab = sm + (size_t)K * XR_ROWS * Wp;       // [Wf][XR_MAXW]
   int* wstart = reinterpret_cast<int*>(wtab + (size_t)Wf * XR_MAXW);  // [Wf]
   int* wcnt = wstart + Wf;                           // [Wf]
+  float* accs = reinterpret_cast<float*>(wcnt + Wf); // BAND: [K][acc_rows][Wf]
   const int b = blockIdx.y, tid = threadIdx.x;
   const long N = (long)H * W;
+  const int band_y0 = BAND ? blockIdx.x * band : 0;
+  const int band_y1 = BAND ? min(H, band_y0 + band) : H;
+  const int i_lo = BAND ? make_lerp(band_y0, sy, Hf).i0 : 0;
+  if constexpr (BAND)
+    for (int e = tid; e < K * acc_rows * Wf; e += XR_THREADS) accs[e] = 0.f;
 
   for (int j = tid; j < Wf; j += XR_THREADS) {
     int lo, hi;
@@ -225,8 +236,8 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
 
   // persistent over the sample's row blocks (the weight tables above are built once per CTA)
   const int vec_per_row = W / 4;
-  for (int y0 = blockIdx.x * XR_ROWS; y0 < H; y0 += gridDim.x * XR_ROWS) {
-  const int rows = min(XR_ROWS, H - y0);
+  for (int y0 = BAND ? band_y0 : blockIdx.x * XR_ROWS; y0 < band_y1; y0 += BAND ? XR_ROWS : gridDim.x * XR_ROWS) {
+  const int rows = min(XR_ROWS, band_y1 - y0);
   __syncthreads();  // tables ready / previous block's readers done
   // ---- phase 1: gradient of ROWS full rows -> shared memory (4 pixels per thread and step) ----
   if constexpr (SRC == 0) {
@@ -312,6 +323,23 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
   __syncthreads();
 
   // ---- phase 2: reduce along x: tmpx[b][k][y][j] = sum_x wx(x, j) dz[k][y][x] ----
+  if constexpr (BAND) {
+    // thread <-> (k, j) column: it alone touches accs[k][*][j]
+    for (int e = tid; e < K * Wf; e += XR_THREADS) {
+      const int k = e / Wf, j = e - k * Wf;
+      const float* wt = wtab + j * XR_MAXW;
+      const int n = wcnt[j], ws = wstart[j];
+      for (int r = 0; r < rows; ++r) {
+        const float* row = dzs + ((size_t)k * XR_ROWS + r) * Wp + ws;
+        float acc = 0.f;
+        for (int q = 0; q < n; ++q) acc = fmaf(wt[q], row[q], acc);
+        const Lerp ly = make_lerp(y0 + r, sy, Hf);
+        float* col = accs + ((long)k * acc_rows - i_lo) * Wf + j;
+        col[(long)ly.i0 * Wf] = fmaf(ly.l0, acc, col[(long)ly.i0 * Wf]);
+        col[(long)ly.i1 * Wf] = fmaf(ly.l1, acc, col[(long)ly.i1 * Wf]);
+      }
+    }
+  } else
   for (int e = tid; e < K * rows * Wf; e += XR_THREADS) {
     const int j = e % Wf;
     const int kr = e / Wf;
@@ -324,6 +352,17 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
     tmpx[(((size_t)b * K + k) * H + y0 + r) * Wf + j] = acc;
   }
   }  // row blocks
+  if constexpr (BAND) {
+    __syncthreads();
+    const int i_hi = make_lerp(band_y1 - 1, sy, Hf).i1;
+    const int nrow = i_hi - i_lo + 1;
+    for (int e = tid; e < K * nrow * Wf; e += XR_THREADS) {
+      const int j = e % Wf;
+      const int kr = e / Wf;
+      const int ri = kr % nrow, k = kr / nrow;
+      atomicAdd(dz_lo + (((size_t)b * K + k) * Hf + i_lo + ri) * Wf + j, accs[((size_t)k * acc_rows + ri) * Wf + j]);
+    }
+  }
 }
 
 // pass 2: dz_lo[b][k][i][j] = sum_y wy(y, i) tmpx[b][k][y][j]
@@ -434,18 +473,51 @@ static int region_extent(int t, float scale, int out_size) {
 
 template <int K, int SRC, int MODE>
 static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int Hf, int Wf, int H, int W, float* dz_lo,
-                          float* tmpx, cudaStream_t st) {
+                          float* tmpx, bool prezeroed, cudaStream_t st) {
   const float sy = H > 1 ? (float)(Hf - 1) / (float)(H - 1) : 0.f;
   const float sx = W > 1 ? (float)(Wf - 1) / (float)(W - 1) : 0.f;
   {
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    bool rows_ok = tmpx != nullptr && W % 4 == 0 && sx > 0.f && 2.0f / sx + 3.0f <= (float)XR_MAXW;
+    bool rows_ok = (tmpx != nullptr || prezeroed) && W % 4 == 0 && sx > 0.f && 2.0f / sx + 3.0f <= (float)XR_MAXW;
     if (SRC == 0) rows_ok = rows_ok && al(dz_hi);
     else rows_ok = rows_ok && al(fa.logits) && al(fa.targets) && fa.t_bstride % 4 == 0 && fa.t_cstride % 4 == 0 &&
                    al(fa.prev_probs) && al(fa.dp_pix) && al(fa.dp_prev);
-    auto kern = dz_rows_xreduce_kernel<K, SRC, MODE>;
     constexpr int ROWS = 2;  // rows per block: small blocks, the persistent loop balances them over one wave
     const size_t smem = ((size_t)K * ROWS * (W + 4) + (size_t)Wf * XR_MAXW + 2 * (size_t)Wf) * sizeof(float);
+    const bool no_band = getenv("RHSEG_NO_BAND_ADJOINT") != nullptr;
+    if (rows_ok && prezeroed && !no_band && sy > 0.f && sy <= 1.0f) {
+      // band kernel: x- and y-reduction in one pass into the pre-zeroed dz_lo
+      auto kern = dz_rows_xreduce_kernel<K, SRC, MODE, true>;
+      const int min_band = (int)ceilf(2.0f / sy) + 1;  // >= taps per low-res row: at most two CTAs feed one row
+      auto smem_for = [&](int band) {
+        const int acc_rows = (int)floorf(sy * (float)band) + 4;
+        return smem + (size_t)K * acc_rows * Wf * sizeof(float);
+      };
+      int per_sm = 0;
+      if (smem_for(min_band) <= 200 * 1024) {
+        const size_t smem0 = smem_for(min_band);
+        if (smem0 > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+        RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, XR_THREADS, smem0));
+      }
+      if (per_sm >= 1) {
+        const long slots = std::max<long>(1, (long)per_sm * device_sm_count() / B);
+        int band = (int)((H + slots - 1) / slots);
+        band = std::max(band, min_band);
+        band = ((band + ROWS - 1) / ROWS) * ROWS;
+        const int acc_rows = (int)floorf(sy * (float)band) + 4;
+        const size_t smem_b = smem_for(band);
+        if (smem_b <= 200 * 1024) {
+          if (smem_b > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+          dim3 grid((unsigned)((H + band - 1) / band), B);
+          launch_pdl(kern, dim3(grid), dim3(XR_THREADS), smem_b, st, dz_hi, fa, Wf, H, W, sx, ROWS, (float*)nullptr, Hf, sy, band,
+                     acc_rows, dz_lo);
+          RHSEG_LAUNCH_CHECK();
+          return RHSEG_OK;
+        }
+      }
+    }
+    if (prezeroed && tmpx == nullptr) rows_ok = false;  // two-kernel row path needs the workspace
+    auto kern = dz_rows_xreduce_kernel<K, SRC, MODE>;
     if (rows_ok && smem <= 200 * 1024) {
       if (smem > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0;
@@ -453,7 +525,7 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
       if (per_sm < 1) per_sm = 1;
       const long slots = std::max<long>(1, (long)per_sm * device_sm_count() / B);
       dim3 grid(balanced_grid((H + ROWS - 1) / ROWS, slots), B);
-      launch_pdl(kern, dim3(grid), dim3(XR_THREADS), smem, st, dz_hi, fa, Wf, H, W, sx, ROWS, tmpx);
+      launch_pdl(kern, dim3(grid), dim3(XR_THREADS), smem, st, dz_hi, fa, Wf, H, W, sx, ROWS, tmpx, Hf, sy, 0, 0, (float*)nullptr);
       RHSEG_LAUNCH_CHECK();
       const long total = (long)B * K * Hf * Wf;
       launch_pdl(yreduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, tmpx, Hf, Wf, H, sy, total, dz_lo);
@@ -480,11 +552,11 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
 using namespace rhseg;
 
 extern "C" int rhseg_upsample_adjoint(const float* dz_hi, int B, int K, int Hf, int Wf, int H, int W, float* dz_lo,
-                                      float* tmp, void* stream) {
+                                      float* tmp, int flags, void* stream) {
   if (!dz_hi || !dz_lo || B <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   FusedDzArgs fa{};
-  RHSEG_DISPATCH_K(K, return (launch_adjoint<KK, 0, 0>(dz_hi, fa, B, Hf, Wf, H, W, dz_lo, tmp, (cudaStream_t)stream)));
+  RHSEG_DISPATCH_K(K, return (launch_adjoint<KK, 0, 0>(dz_hi, fa, B, Hf, Wf, H, W, dz_lo, tmp, (flags & RHSEG_DZ_PREZEROED) != 0, (cudaStream_t)stream)));
   return RHSEG_OK;
 }
 
@@ -493,17 +565,18 @@ extern "C" int rhseg_head_dz_lowres_fused(const float* logits, const float* targ
                                           const float* prev_probs, const int32_t* table, const double* g_uniform,
                                           double inv_npix, const float* dp_pix, uint32_t pix_mask, int B, int K,
                                           int K_prev, int Hf, int Wf, int H, int W, int act_mode, float* dz_lo,
-                                          float* dp_prev, float* tmp, void* stream) {
+                                          float* dp_prev, float* tmp, int flags, void* stream) {
   if (!logits || !targets || !coef || !dz_lo || B <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   if (act_mode == RHSEG_ACT_GROUPED && (!prev_probs || !table)) return RHSEG_ERR_ARG;
   FusedDzArgs fa{logits, targets, t_bstride, t_cstride, coef, g_ce, g_dice, prev_probs, table, g_uniform,
                  (float)inv_npix, dp_pix, pix_mask, dp_prev, K_prev};
   cudaStream_t st = (cudaStream_t)stream;
+  const bool pz = (flags & RHSEG_DZ_PREZEROED) != 0;
   RHSEG_DISPATCH_K(K, {
-    if (act_mode == RHSEG_ACT_SIGMOID) return launch_adjoint<KK, 1, RHSEG_ACT_SIGMOID>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, st);
-    if (act_mode == RHSEG_ACT_GROUPED) return launch_adjoint<KK, 1, RHSEG_ACT_GROUPED>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, st);
-    return launch_adjoint<KK, 1, RHSEG_ACT_ZEROS>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, st);
+    if (act_mode == RHSEG_ACT_SIGMOID) return launch_adjoint<KK, 1, RHSEG_ACT_SIGMOID>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, pz, st);
+    if (act_mode == RHSEG_ACT_GROUPED) return launch_adjoint<KK, 1, RHSEG_ACT_GROUPED>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, pz, st);
+    return launch_adjoint<KK, 1, RHSEG_ACT_ZEROS>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, pz, st);
   });
   return RHSEG_OK;
 }

@@ -75,11 +75,10 @@ class _FusedStepFn(torch.autograd.Function):
         for k in tree.head_channels:
             ch_off.append(ch_off[-1] + k)
         offs, words = _eval_layout(tree, B)
-        ws = torch.zeros((words,), dtype=torch.float64, device=dev)  # one fill; the eval kernels are told it is zeroed
         idx_maps = [torch.empty((B,) + tuple(target.shape[2:]), dtype=torch.uint8, device=dev) if L < n - 1 else None
                     for L in range(n)]
 
-        def evaluate(L, dims):
+        def evaluate(L, dims, ws):  # ws: the zeroed statistics workspace (part of the forward's single fill)
             if dims[0] != B or (dims[4], dims[5]) != tuple(target.shape[2:]):
                 raise native.NativeError("target %s does not match the head output [%d, *, %d, %d]"
                                          % (tuple(target.shape), dims[0], dims[4], dims[5]))
@@ -87,7 +86,8 @@ class _FusedStepFn(torch.autograd.Function):
                     target.data_ptr() + ch_off[L - 1] * t_cs * esz if L > 0 else None,
                     ptr(idx_maps[L - 1]) if L > 0 else None, ws.data_ptr() + offs[L][0] * 8, ptr(idx_maps[L]))
 
-        r = forward_levels(tree, out_size, tensors, evaluate)
+        r = forward_levels(tree, out_size, tensors, evaluate, zero_words=words)
+        ws = r["workspace"]
         B, C, Hf, Wf, H, W = r["dims"]
         st = stream_of(r["feats"][0])
         n_pix = H * W
@@ -138,7 +138,10 @@ class _FusedStepFn(torch.autograd.Function):
         n_pix = H * W
         g = g_total.reshape(1)
         g = g if g.dtype == torch.float32 else g.float()
-        sums = alloc_weight_sums(tree, B, C, dev)
+        if ctx.upsampled:
+            sums, dz_zero = alloc_weight_sums(tree, B, C, dev, (Hf, Wf))
+        else:
+            sums, dz_zero = alloc_weight_sums(tree, B, C, dev), None
         d_feats: List[Optional[torch.Tensor]] = [None] * n
         d_hw: List[Optional[torch.Tensor]] = [None] * n
         d_hb: List[Optional[torch.Tensor]] = [None] * n
@@ -162,11 +165,11 @@ class _FusedStepFn(torch.autograd.Function):
             t_ptr = target.data_ptr() + ch_off[L] * t_cs * esz
             c_ptr = coef_all.data_ptr() + coef_offs[L] * 4
             if ctx.upsampled:
-                dz = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev)
-                tmpx = torch.empty((B, K, H, Wf), dtype=torch.float32, device=dev)
+                dz = dz_zero[L]  # zeroed together with the weight sums: the band kernel adds into it
+                tmpx = torch.empty((B, K, H, Wf), dtype=torch.float32, device=dev)  # only touched by the fallback kernels
                 call("rhseg_head_dz_lowres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, ptr(g), ptr(g),
                      ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]), ptr(g_uniform), 1.0 / n_pix, ptr(dp_pix),
-                     pix_mask, B, K, K_prev, Hf, Wf, H, W, mode, ptr(dz), ptr(dp_prev), ptr(tmpx), st)
+                     pix_mask, B, K, K_prev, Hf, Wf, H, W, mode, ptr(dz), ptr(dp_prev), ptr(tmpx), native.DZ_PREZEROED, st)
             else:
                 dz = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
                 call("rhseg_head_dz_fullres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, ptr(g), ptr(g),

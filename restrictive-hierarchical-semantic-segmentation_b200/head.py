@@ -35,13 +35,15 @@ def _side_stream(dev):
     return _SIDE_STREAMS[key]
 
 
-def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
+def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words: int = 0):
     """Runs the per-level forward kernels.  `tensors` = feats[n] + head_w[n] + head_b[n] + film_w[n-1] +
     film_b[n-1].  Returns a dict with the inputs (contiguous fp32) and probs / logits / psums / eff_w /
     gamma_beta per level plus the shape tuple.
     `evaluate(L, dims)` (fused training step) returns the rhseg_level_eval arguments of level L:
     (targets_ptr, t_bs, t_cs, parent_ptr, prev_idx_ptr, out_words_ptr, idx_out_ptr); the evaluation then runs
-    inside the hi-res forward kernel (upsampled heads) or right after the level's forward (feature-resolution heads)."""
+    inside the hi-res forward kernel (upsampled heads) or right after the level's forward (feature-resolution heads).
+    `zero_words` extra fp64 words are zeroed by the same fill as the pool sums / low-res logits and handed to
+    `evaluate` as its third argument (the fused step's statistics workspace)."""
     n = tree.num_levels
     feats = [_f32c(t) for t in tensors[0:n]]
     head_w = [_f32c(t) for t in tensors[n:2 * n]]
@@ -57,12 +59,17 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
     upsampled = (H, W) != (Hf, Wf)
     n_pix = H * W
     probs, logits, psums, eff_ws, gbs = [], [], [], [], []
-    # every level's fp64 pool sums live in one buffer zeroed by a single fill
-    psum_all = torch.zeros((sum(tree.head_channels) * B,), dtype=torch.float64, device=dev)
+    # ONE zero fill per forward: every level's fp64 pool sums | the caller's workspace | the low-res logits of
+    # all levels (fp32; tiles split between CTAs accumulate into them)
+    n_psum = sum(tree.head_channels) * B
+    n_zlo = B * sum(tree.head_channels) * Hf * Wf if upsampled else 0
+    n_head = (n_psum + int(zero_words) + 1) // 2 * 2  # the fp32 tail starts 16-byte aligned, as a separate allocation would
+    zero_all = torch.zeros((n_head + (n_zlo + 1) // 2,), dtype=torch.float64, device=dev)
+    psum_all = zero_all[:n_psum]
+    workspace = zero_all[n_psum:n_psum + int(zero_words)]
+    zlo_all = zero_all[n_head:].view(torch.float32) if upsampled else None
     psum_off = 0
     used_side = False
-    # low-res logits of all levels in one zero-filled buffer (tiles split between CTAs accumulate into it)
-    zlo_all = torch.zeros((B * sum(tree.head_channels) * Hf * Wf,), dtype=torch.float32, device=dev) if upsampled else None
     zlo_off = 0
     for L in range(n):
         K = tree.head_channels[L]
@@ -88,7 +95,7 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
         if upsampled:
             z_lo = zlo_all[zlo_off:zlo_off + B * K * Hf * Wf].view(B, K, Hf, Wf)
             zlo_off += B * K * Hf * Wf
-        ev = evaluate(L, (B, C, Hf, Wf, H, W)) if evaluate is not None else None
+        ev = evaluate(L, (B, C, Hf, Wf, H, W), workspace) if evaluate is not None else None
         # The evaluation of level L only needs its logits (and the previous level's index map): for all
         # but the last level it runs on a side stream, overlapping the (memory-bound) forward of the next
         # level; the last level's evaluation is fused into its hi-res forward kernel when there is one.
@@ -125,7 +132,7 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None):
     if used_side:
         torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
     return dict(feats=feats, head_w=head_w, head_b=head_b, film_w=film_w, film_b=film_b, probs=probs, logits=logits,
-                psums=psums, eff_ws=eff_ws, gbs=gbs, dims=(B, C, Hf, Wf, H, W), upsampled=upsampled)
+                psums=psums, eff_ws=eff_ws, gbs=gbs, dims=(B, C, Hf, Wf, H, W), upsampled=upsampled, workspace=workspace)
 
 
 def level_weight_backward(tree, L, dims, feats_L, dz_feat, eff_w_L, head_w_L, film_w_prev, gb_L, psum_prev, S, s,
@@ -152,15 +159,26 @@ def level_weight_backward(tree, L, dims, feats_L, dz_feat, eff_w_L, head_w_L, fi
     return d_feats, d_hw, d_hb, d_fw, d_fb, g_prev
 
 
-def alloc_weight_sums(tree, B, C, dev):
-    """One zero-filled fp64 buffer holding S [B,K,C] and s [B,K] of every level; returns per-level views."""
+def alloc_weight_sums(tree, B, C, dev, lowres_hw=None):
+    """One zero-filled fp64 buffer holding S [B,K,C] and s [B,K] of every level; returns per-level views.
+    With lowres_hw = (Hf, Wf) the same fill also zeroes one fp32 dz_lo [B,K,Hf,Wf] per level (the band adjoint
+    kernel adds into a pre-zeroed buffer, RHSEG_DZ_PREZEROED) and (views, dz_views) is returned."""
     total = sum(B * k * (C + 1) for k in tree.head_channels)
-    buf = torch.zeros((total,), dtype=torch.float64, device=dev)
+    total += total & 1  # keep the fp32 tail 16-byte aligned
+    n_lo = 0 if lowres_hw is None else lowres_hw[0] * lowres_hw[1]
+    lo_words = [(B * k * n_lo + 3) // 4 * 2 for k in tree.head_channels]  # fp64 words per level, 16-byte multiples
+    buf = torch.zeros((total + sum(lo_words),), dtype=torch.float64, device=dev)
     views, off = [], 0
     for k in tree.head_channels:
         views.append((buf[off:off + B * k * C].view(B, k, C), buf[off + B * k * C:off + B * k * (C + 1)].view(B, k)))
         off += B * k * (C + 1)
-    return views
+    if lowres_hw is None:
+        return views
+    dz_views, off = [], total
+    for k, w in zip(tree.head_channels, lo_words):
+        dz_views.append(buf[off:off + w].view(torch.float32)[:B * k * n_lo].view(B, k, lowres_hw[0], lowres_hw[1]))
+        off += w
+    return views, dz_views
 
 
 class _HierHeadFn(torch.autograd.Function):
@@ -198,7 +216,10 @@ class _HierHeadFn(torch.autograd.Function):
         d_fw: List[Optional[torch.Tensor]] = [None] * (n - 1)
         d_fb: List[Optional[torch.Tensor]] = [None] * (n - 1)
 
-        sums = alloc_weight_sums(tree, B, C, dev)
+        if ctx.upsampled:
+            sums, dz_zero = alloc_weight_sums(tree, B, C, dev, (Hf, Wf))
+        else:
+            sums, dz_zero = alloc_weight_sums(tree, B, C, dev), None
         g_uniform = None   # [B,K_L] fp64: dLoss/d(sum_n P_L) * n_pix, from level L+1's FiLM
         dp_pix = None      # [B,K_L,H,W]: per-pixel dLoss/dP_L (composition of level L+1 and/or user grads)
         pix_mask = 0
@@ -231,9 +252,9 @@ class _HierHeadFn(torch.autograd.Function):
             if dz is None:
                 continue  # nothing reaches this level's logits: no gradient for its features / parameters
             if ctx.upsampled:
-                dz_lo = torch.empty((B, K, Hf, Wf), dtype=torch.float32, device=dev)
+                dz_lo = dz_zero[L]  # zeroed together with the weight sums
                 tmpx = torch.empty((B, K, H, Wf), dtype=torch.float32, device=dev)
-                call("rhseg_upsample_adjoint", ptr(dz), B, K, Hf, Wf, H, W, ptr(dz_lo), ptr(tmpx), st)
+                call("rhseg_upsample_adjoint", ptr(dz), B, K, Hf, Wf, H, W, ptr(dz_lo), ptr(tmpx), native.DZ_PREZEROED, st)
                 dz = dz_lo
             S, s = sums[L]
             d_feats[L], d_hw[L], d_hb[L], fw_g, fb_g, g_prev = level_weight_backward(

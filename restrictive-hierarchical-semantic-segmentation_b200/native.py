@@ -16,6 +16,7 @@ KERNEL_MAX_K = 8
 TABLE_INTS = 4 + 5 * MAX_K
 NSTAT = 5
 XCHG_HANDLE_BYTES = 64
+DZ_PREZEROED = 1
 ACT_SIGMOID, ACT_GROUPED, ACT_ZEROS = 0, 1, 2
 
 _c = ctypes
@@ -32,8 +33,8 @@ SIGNATURES = {
     "rhseg_head_level_fwd_eval": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P,
                                   _P, _L, _L, _P, _L, _L, _P, _P, _P, _I, _P],
     "rhseg_head_act_bwd": [_P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _I, _P, _P, _P],
-    "rhseg_upsample_adjoint": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
-    "rhseg_head_dz_lowres_fused": [_P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "rhseg_upsample_adjoint": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P],
+    "rhseg_head_dz_lowres_fused": [_P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "rhseg_pack_f64": [_P, _P, _I, _P, _P],
     "rhseg_unpack_f32": [_P, _D, _P, _P, _I, _P],
     "rhseg_xchg_create": [_L, _I, _P, _P],

@@ -136,3 +136,35 @@ def test_concat_image_logits_utility(shape):
     x, z = torch.randn(B, ci, H, W, generator=g), torch.randn(B, K, H, W, generator=g)
     got = rhseg_b200.concat_image_logits(x.to(DEV), z.to(DEV))
     assert torch.equal(got.cpu(), torch.cat([x, z], dim=1))
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 10, 12, 40, 48), (1, 4, 155, 155, 620, 620), (3, 1, 7, 9, 21, 28), (2, 8, 6, 8, 24, 32),
+                                   (1, 2, 5, 5, 5, 8), (1, 2, 6, 8, 50, 16), (5, 4, 9, 7, 33, 20), (1, 3, 2, 3, 7, 12)],
+                         ids=lambda s: "B%d_K%d_%dx%d_to_%dx%d" % s)
+def test_upsample_adjoint_kernels_agree_with_autograd(shape):
+    """The three adjoint kernels (band kernel into a pre-zeroed buffer, row kernel + y-reduction, tiled kernel)
+    against autograd through F.interpolate(bilinear, align_corners=True) in fp64."""
+    from rhseg_b200 import native
+    from rhseg_b200.native import call, ptr
+    B, K, Hf, Wf, H, W = shape
+    g = torch.Generator().manual_seed(7 + sum(shape))
+    dz_hi = torch.randn(B, K, H, W, generator=g)
+    x = torch.zeros(B, K, Hf, Wf, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.interpolate(x, size=(H, W), mode="bilinear", align_corners=True).backward(dz_hi.double())
+    want = x.grad.float()
+    d = dz_hi.to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    tmp = torch.empty(B, K, H, Wf, device=DEV)
+    outs = {}
+    outs["band"] = torch.zeros(B, K, Hf, Wf, device=DEV)
+    call("rhseg_upsample_adjoint", ptr(d), B, K, Hf, Wf, H, W, ptr(outs["band"]), None, native.DZ_PREZEROED, st)
+    outs["rows"] = torch.full((B, K, Hf, Wf), float("nan"), device=DEV)
+    call("rhseg_upsample_adjoint", ptr(d), B, K, Hf, Wf, H, W, ptr(outs["rows"]), ptr(tmp), 0, st)
+    outs["tiled"] = torch.full((B, K, Hf, Wf), float("nan"), device=DEV)
+    call("rhseg_upsample_adjoint", ptr(d), B, K, Hf, Wf, H, W, ptr(outs["tiled"]), None, 0, st)
+    for name, got in outs.items():
+        close(got, want, what="adjoint[%s]" % name)
+    # the band kernel is deterministic (at most two CTAs add into a row)
+    again = torch.zeros(B, K, Hf, Wf, device=DEV)
+    call("rhseg_upsample_adjoint", ptr(d), B, K, Hf, Wf, H, W, ptr(again), None, native.DZ_PREZEROED, st)
+    assert torch.equal(again, outs["band"])
