@@ -488,28 +488,38 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
     if (rows_ok && prezeroed && !no_band && sy > 0.f && sy <= 1.0f) {
       // band kernel: x- and y-reduction in one pass into the pre-zeroed dz_lo
       auto kern = dz_rows_xreduce_kernel<K, SRC, MODE, true>;
-      const int min_band = (int)ceilf(2.0f / sy) + 1;  // >= taps per low-res row: at most two CTAs feed one row
+      // >= taps per low-res row (ceil(2/sy) - 1 would do): at most two CTAs feed one low-res row
+      const int min_band = std::max(2, (int)ceilf(2.0f / sy));
+      // rows per phase-1 pass: the one that wastes the fewest threads (a pass handles rows * W/4 four-pixel items
+      // with XR_THREADS threads: 2 rows of 620 px keep only 60 % of them busy, 3 rows 91 %)
+      const int vpr = W / 4;
+      int sub = 1;
+      double best_util = 0.0;
+      for (int r = 1; r <= 4; ++r) {
+        const int items = r * vpr;
+        const double util = (double)items / (double)(((items + XR_THREADS - 1) / XR_THREADS) * XR_THREADS);
+        if (util > best_util + 1e-9) { best_util = util; sub = r; }
+      }
       auto smem_for = [&](int band) {
         const int acc_rows = (int)floorf(sy * (float)band) + 4;
-        return smem + (size_t)K * acc_rows * Wf * sizeof(float);
+        return ((size_t)K * sub * (W + 4) + (size_t)Wf * XR_MAXW + 2 * (size_t)Wf + (size_t)K * acc_rows * Wf) * sizeof(float);
       };
+      auto round_band = [&](int band) { return ((std::max(band, min_band) + sub - 1) / sub) * sub; };
       int per_sm = 0;
-      if (smem_for(min_band) <= 200 * 1024) {
-        const size_t smem0 = smem_for(min_band);
+      const size_t smem0 = smem_for(round_band(min_band));
+      if (smem0 <= 200 * 1024) {
         if (smem0 > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
         RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, XR_THREADS, smem0));
       }
       if (per_sm >= 1) {
         const long slots = std::max<long>(1, (long)per_sm * device_sm_count() / B);
-        int band = (int)((H + slots - 1) / slots);
-        band = std::max(band, min_band);
-        band = ((band + ROWS - 1) / ROWS) * ROWS;
+        const int band = round_band((int)((H + slots - 1) / slots));
         const int acc_rows = (int)floorf(sy * (float)band) + 4;
         const size_t smem_b = smem_for(band);
         if (smem_b <= 200 * 1024) {
           if (smem_b > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
           dim3 grid((unsigned)((H + band - 1) / band), B);
-          launch_pdl(kern, dim3(grid), dim3(XR_THREADS), smem_b, st, dz_hi, fa, Wf, H, W, sx, ROWS, (float*)nullptr, Hf, sy, band,
+          launch_pdl(kern, dim3(grid), dim3(XR_THREADS), smem_b, st, dz_hi, fa, Wf, H, W, sx, sub, (float*)nullptr, Hf, sy, band,
                      acc_rows, dz_lo);
           RHSEG_LAUNCH_CHECK();
           return RHSEG_OK;
