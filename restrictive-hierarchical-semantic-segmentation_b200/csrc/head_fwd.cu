@@ -496,7 +496,9 @@ upsample_act_tiled_kernel(const float* __restrict__ z_lo, const float* __restric
   pdl_wait();
   constexpr int TH = 16, TW = 16 * VEC;
   constexpr int PH = TH + 2, PW = TW + 2;  // patch bound for scale <= 1
-  __shared__ float patch[K][PH][PW];
+  // double buffered when it fits the static limit: the next tile's patch streams in (cp.async) while this one is used
+  constexpr int NBUF = (2 * K * PH * PW * 4 <= 40 * 1024) ? 2 : 1;
+  __shared__ float patch2[NBUF][K][PH][PW];
   __shared__ float red[8 * K];
   __shared__ float ered[EVAL ? 8 * EvalAccum<K>::NACC : 1];
   __shared__ int hist[EVAL ? (K + 1) * (K + 1) : 1];
@@ -511,24 +513,40 @@ upsample_act_tiled_kernel(const float* __restrict__ z_lo, const float* __restric
 #pragma unroll
   for (int k = 0; k < K; ++k) ps[k] = 0.f;
 
-  // persistent over the sample's tiles: pool sums / evaluation statistics are reduced once per CTA
-  for (int tile = blockIdx.x; tile < tiles_per_sample; tile += gridDim.x) {
+  // low-res support of one tile -> shared memory, asynchronously (4-byte cp.async: HRNet planes are only 4-byte aligned)
+  auto issue_patch = [&](int tile, int buf) {
     const int ty0 = (tile / tiles_x) * TH, tx0 = (tile % tiles_x) * TW;
     const int ylast = min(ty0 + TH, H) - 1, xlast = min(tx0 + TW, W) - 1;
     const int r0 = (int)(sy * (float)ty0), c0 = (int)(sx * (float)tx0);
     const int r1 = min((int)(sy * (float)ylast) + 1, Hf - 1), c1 = min((int)(sx * (float)xlast) + 1, Wf - 1);
     const int ph = r1 - r0 + 1, pw = c1 - c0 + 1;
-    __syncthreads();  // previous tile's readers are done with the patch
-    {
-      const int lane = tid & 31, warp = tid >> 5;
-      for (int rr = warp; rr < ph; rr += 8)
-        for (int cc = lane; cc < pw; cc += 32) {
-          const float* src = zb + (size_t)(r0 + rr) * Wf + c0 + cc;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int rr = warp; rr < ph; rr += 8)
+      for (int cc = lane; cc < pw; cc += 32) {
+        const float* src = zb + (size_t)(r0 + rr) * Wf + c0 + cc;
 #pragma unroll
-          for (int k = 0; k < K; ++k) patch[k][rr][cc] = __ldg(src + (size_t)k * Nf);
+        for (int k = 0; k < K; ++k) {
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&patch2[buf][k][rr][cc]);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + (size_t)k * Nf) : "memory");
         }
+      }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // persistent over the sample's tiles: pool sums / evaluation statistics are reduced once per CTA
+  int buf = 0;
+  if (NBUF == 2 && (int)blockIdx.x < tiles_per_sample) issue_patch(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < tiles_per_sample; tile += gridDim.x, buf ^= (NBUF - 1)) {
+    const int ty0 = (tile / tiles_x) * TH, tx0 = (tile % tiles_x) * TW;
+    const int r0 = (int)(sy * (float)ty0), c0 = (int)(sx * (float)tx0);
+    if constexpr (NBUF == 1) {
+      __syncthreads();  // previous tile's readers are done with the patch
+      issue_patch(tile, 0);
     }
-    __syncthreads();
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();  // this tile's patch has landed; everybody is done reading the other buffer
+    if (NBUF == 2 && tile + (int)gridDim.x < tiles_per_sample) issue_patch(tile + gridDim.x, buf ^ 1);
+    float (*patch)[PH][PW] = patch2[buf];
     const int y = ty0 + (tid >> 4), x0 = tx0 + (tid & 15) * VEC;
     const bool ok = y < H && x0 < W;  // W % VEC == 0 guaranteed by the launcher
     const long px = (long)y * W + x0;
