@@ -173,12 +173,13 @@ int rhseg_head_conv_bwd(const float* feats, const float* dz, const float* eff_w,
  *   d_head_w [K,C], d_head_b [K]; and when film_w != NULL: d_film_w [2C,K_prev],
  *   d_film_b [2C], g_prev [B,K_prev] fp64 = film_w^T [dgamma|dbeta]  (the uniform gradient
  *   w.r.t. the previous level's pooled probabilities, before the 1/n_pix).
- * gamma_beta [B,2C] and prev_psum [B,K_prev] are the forward's.                           */
+ * gamma_beta [B,2C] and prev_psum [B,K_prev] are the forward's.  g_prev is accumulated with
+ * atomics: zeroed here unless g_prev_zeroed != 0 (the caller passes a zeroed buffer).        */
 int rhseg_head_param_grads(const double* S, const double* s, const float* head_w,
                            const float* film_w, const float* gamma_beta, const double* prev_psum,
                            double n_pix, int B, int C, int K, int K_prev,
                            float* d_head_w, float* d_head_b, float* d_film_w, float* d_film_b,
-                           double* g_prev, void* stream);
+                           double* g_prev, int g_prev_zeroed, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (3) hierarchical loss.  Replaces CrossEntropyLoss / SoftDiceLoss (Metrics/losses.py:16-134)

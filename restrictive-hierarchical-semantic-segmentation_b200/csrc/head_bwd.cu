@@ -552,14 +552,14 @@ extern "C" int rhseg_head_conv_bwd(const float* feats, const float* dz, const fl
 extern "C" int rhseg_head_param_grads(const double* S, const double* s, const float* head_w, const float* film_w,
                                       const float* gamma_beta, const double* prev_psum, double n_pix, int B, int C,
                                       int K, int K_prev, float* d_head_w, float* d_head_b, float* d_film_w,
-                                      float* d_film_b, double* g_prev, void* stream) {
+                                      float* d_film_b, double* g_prev, int g_prev_zeroed, void* stream) {
   if (!S || !s || !head_w || !d_head_w || !d_head_b || B <= 0 || C <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   if (film_w) {
     if (!gamma_beta || !prev_psum || !d_film_w || !d_film_b || !g_prev || n_pix <= 0) return RHSEG_ERR_ARG;
     if (K_prev < 1 || K_prev > RHSEG_MAX_K) return RHSEG_ERR_UNSUPPORTED;
-    RHSEG_CUDA(cudaMemsetAsync(g_prev, 0, sizeof(double) * (size_t)B * K_prev, st));
+    if (!g_prev_zeroed) RHSEG_CUDA(cudaMemsetAsync(g_prev, 0, sizeof(double) * (size_t)B * K_prev, st));
   }
   launch_pdl(param_grads_kernel, dim3((C + PG_CH - 1) / PG_CH), dim3(PG_THREADS), 0, st, S, s, head_w, film_w, gamma_beta, prev_psum, n_pix, B, C, K, K_prev,
                                                       d_head_w, d_head_b, d_film_w, d_film_b, g_prev);

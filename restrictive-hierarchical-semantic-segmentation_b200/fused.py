@@ -175,10 +175,10 @@ class _FusedStepFn(torch.autograd.Function):
                 call("rhseg_head_dz_fullres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, ptr(g), ptr(g),
                      ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]), ptr(g_uniform), 1.0 / n_pix, ptr(dp_pix),
                      pix_mask, B, K, K_prev, n_pix, mode, ptr(dz), ptr(dp_prev), st)
-            S, s = sums[L]
+            S, s, gp0 = sums[L]
             d_feats[L], d_hw[L], d_hb[L], fw_g, fb_g, g_prev = level_weight_backward(
                 tree, L, ctx.dims, feats[L], dz, eff_ws[L], head_w[L], film_w[L - 1] if L > 0 else None, gbs[L],
-                psums[L - 1] if L > 0 else None, S, s, ctx.needs_input_grad[6 + L], st)
+                psums[L - 1] if L > 0 else None, S, s, ctx.needs_input_grad[6 + L], st, gp0)
             if L > 0:
                 d_fw[L - 1], d_fb[L - 1] = fw_g, fb_g
             g_uniform, dp_pix, pix_mask = g_prev, dp_prev, prev_mask

@@ -136,7 +136,7 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words
 
 
 def level_weight_backward(tree, L, dims, feats_L, dz_feat, eff_w_L, head_w_L, film_w_prev, gb_L, psum_prev, S, s,
-                          want_dfeats, st):
+                          want_dfeats, st, g_prev_zeroed=None):
     """conv backward + parameter gradients of one level given dz at feature resolution.
     Returns (d_feats or None, d_head_w, d_head_b, d_film_w or None, d_film_b or None, g_prev or None)."""
     B, C, Hf, Wf, H, W = dims
@@ -152,26 +152,30 @@ def level_weight_backward(tree, L, dims, feats_L, dz_feat, eff_w_L, head_w_L, fi
     if L > 0:
         d_fw = torch.empty_like(film_w_prev)
         d_fb = torch.empty((2 * C,), dtype=torch.float32, device=dev)
-        g_prev = torch.empty((B, K_prev), dtype=torch.float64, device=dev)
+        # the pool-gradient accumulator: a zeroed slice of the weight-sum buffer when the caller has one
+        g_prev = g_prev_zeroed if g_prev_zeroed is not None else torch.empty((B, K_prev), dtype=torch.float64, device=dev)
     call("rhseg_head_param_grads", ptr(S), ptr(s), ptr(head_w_L), ptr(film_w_prev) if L > 0 else None, ptr(gb_L),
          ptr(psum_prev) if L > 0 else None, float(H * W), B, C, K, K_prev, ptr(d_hw), ptr(d_hb),
-         ptr(d_fw), ptr(d_fb), ptr(g_prev), st)
+         ptr(d_fw), ptr(d_fb), ptr(g_prev), 1 if g_prev_zeroed is not None else 0, st)
     return d_feats, d_hw, d_hb, d_fw, d_fb, g_prev
 
 
 def alloc_weight_sums(tree, B, C, dev, lowres_hw=None):
-    """One zero-filled fp64 buffer holding S [B,K,C] and s [B,K] of every level; returns per-level views.
+    """One zero-filled fp64 buffer holding S [B,K,C], s [B,K] and the pool-gradient accumulator g_prev [B,K_prev]
+    of every level; returns per-level views (S, s, g_prev or None).
     With lowres_hw = (Hf, Wf) the same fill also zeroes one fp32 dz_lo [B,K,Hf,Wf] per level (the band adjoint
     kernel adds into a pre-zeroed buffer, RHSEG_DZ_PREZEROED) and (views, dz_views) is returned."""
-    total = sum(B * k * (C + 1) for k in tree.head_channels)
+    kprev = [0] + list(tree.head_channels[:-1])
+    total = sum(B * k * (C + 1) + B * kp for k, kp in zip(tree.head_channels, kprev))
     total += total & 1  # keep the fp32 tail 16-byte aligned
     n_lo = 0 if lowres_hw is None else lowres_hw[0] * lowres_hw[1]
     lo_words = [(B * k * n_lo + 3) // 4 * 2 for k in tree.head_channels]  # fp64 words per level, 16-byte multiples
     buf = torch.zeros((total + sum(lo_words),), dtype=torch.float64, device=dev)
     views, off = [], 0
-    for k in tree.head_channels:
-        views.append((buf[off:off + B * k * C].view(B, k, C), buf[off + B * k * C:off + B * k * (C + 1)].view(B, k)))
-        off += B * k * (C + 1)
+    for k, kp in zip(tree.head_channels, kprev):
+        gp = buf[off + B * k * (C + 1):off + B * k * (C + 1) + B * kp].view(B, kp) if kp else None
+        views.append((buf[off:off + B * k * C].view(B, k, C), buf[off + B * k * C:off + B * k * (C + 1)].view(B, k), gp))
+        off += B * k * (C + 1) + B * kp
     if lowres_hw is None:
         return views
     dz_views, off = [], total
@@ -256,10 +260,10 @@ class _HierHeadFn(torch.autograd.Function):
                 tmpx = torch.empty((B, K, H, Wf), dtype=torch.float32, device=dev)
                 call("rhseg_upsample_adjoint", ptr(dz), B, K, Hf, Wf, H, W, ptr(dz_lo), ptr(tmpx), native.DZ_PREZEROED, st)
                 dz = dz_lo
-            S, s = sums[L]
+            S, s, gp0 = sums[L]
             d_feats[L], d_hw[L], d_hb[L], fw_g, fb_g, g_prev = level_weight_backward(
                 tree, L, ctx.dims, feats[L], dz, eff_ws[L], head_w[L], film_w[L - 1] if L > 0 else None, gbs[L],
-                psums[L - 1] if L > 0 else None, S, s, ctx.needs_input_grad[2 + L], st)
+                psums[L - 1] if L > 0 else None, S, s, ctx.needs_input_grad[2 + L], st, gp0)
             if L > 0:
                 d_fw[L - 1], d_fb[L - 1] = fw_g, fb_g
             g_uniform = g_prev
