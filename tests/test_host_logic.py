@@ -205,6 +205,22 @@ def _dist_worker(rank, world, port, q):
         ok &= all(torch.equal(a, b) for a, b in zip(got["confusion"], ref_conf))
         ok &= abs(float(got["dice"][1]) - float(ref_scal[3 + 4])) < 1e-6 and float(got["n_dice"][1]) == 3.0
         scale = rdist.dice_grad_scale(scal[4 + 4].double(), got["n_dice"][1], world)
+        # exchange-buffer form ([summary | parameter gradients], one all-reduce): host logic on CPU tensors
+        summ = rdist.pack_step_summary(scal, hi - lo, conf)
+        grads = [torch.full((3, 2), float(rank + 1)), torch.arange(5, dtype=torch.float32) * (rank + 1)]
+        buf = rdist.pack_exchange(summ, grads)
+        ok &= buf.dtype == torch.float64 and buf.numel() == summ.numel() + 11
+        dist.all_reduce(buf)
+        back = [torch.zeros(3, 2), torch.zeros(5)]
+        rdist.unpack_exchange(buf, summ.numel(), back, scale=1.0 / world)
+        ok &= bool(torch.equal(back[0], torch.full((3, 2), 1.5))) and bool(torch.equal(back[1], torch.arange(5, dtype=torch.float32) * 1.5))
+        glob = rdist.unpack_global(buf, len(logits), [tuple(c.shape) for c in conf])
+        ok &= abs(float(glob["total"]) - float(ref_scal[0])) < 1e-5
+        try:  # the peer-memory exchange is CUDA-only and says so
+            rdist.PeerExchange(16)
+            ok = False
+        except Exception as e:
+            ok &= "NativeError" in type(e).__name__ or "CUDA" in str(e) or "cuda" in str(e)
         q.put((rank, bool(ok), float(scale)))
     finally:
         dist.destroy_process_group()
