@@ -206,6 +206,16 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 __device__ __forceinline__ float sigmoidf_ref(float z) { return rcp_approx(1.0f + __expf(-z)); }
 
+// x / y for the tiny latency-bound kernels (finalize, parameter gradients): fp32 reciprocal seed + two Newton steps
+// in fp64 (~1 ulp) instead of the ~40-instruction IEEE division routine on the critical thread.  y == 0 gives NaN
+// (callers treat 0/0 as "invalid", as IEEE does; x/0 with x != 0 does not occur there).
+__device__ __forceinline__ double fast_div(double x, double y) {
+  double r = (double)__frcp_rn((float)y);
+  r = r * (2.0 - y * r);
+  r = r * (2.0 - y * r);
+  return x * r;
+}
+
 // Segmented (per contiguous group) softmax over K channels; groups start where start_mask has a bit.
 template <int K>
 __device__ __forceinline__ void grouped_softmax(const float (&z)[K], int start_mask, float (&q)[K]) {

@@ -395,7 +395,7 @@ param_grads_kernel(const double* __restrict__ S, const double* __restrict__ s, c
   pdl_wait();
   constexpr int NV = RHSEG_KERNEL_MAX_K + 2 + 2 * RHSEG_MAX_K;  // dw[k], dfb_g, dfb_b, dfw_g[j], dfw_b[j]
   __shared__ float red[PG_BL][PG_CH][NV + 1];
-  __shared__ float gsm[PG_THREADS / 32];
+  __shared__ float gsm[PG_THREADS / 32][RHSEG_MAX_K];
   const int cl = threadIdx.x % PG_CH, bl = threadIdx.x / PG_CH;
   const int c = blockIdx.x * PG_CH + cl;
   const bool ok = c < C;
@@ -435,20 +435,20 @@ param_grads_kernel(const double* __restrict__ S, const double* __restrict__ s, c
       acc[RHSEG_KERNEL_MAX_K] += (float)dgam;
       acc[RHSEG_KERNEL_MAX_K + 1] += (float)dbet;
       for (int j = 0; j < K_prev; ++j) {
-        const double cond = b < B ? (double)(float)(prev_psum[b * K_prev + j] / n_pix) : 0.0;
+        const double cond = b < B ? (double)(float)fast_div(prev_psum[b * K_prev + j], n_pix) : 0.0;
         acc[RHSEG_KERNEL_MAX_K + 2 + j] += (float)(dgam * cond);
         acc[RHSEG_KERNEL_MAX_K + 2 + RHSEG_MAX_K + j] += (float)(dbet * cond);
-        // g_prev[b][j] = sum over channels of film_w^T [dgamma|dbeta]: the two warps that share (bl) reduce
+        // g_prev[b][j] = sum over channels of film_w^T [dgamma|dbeta]: warp sums now, one block step below
         const float contrib = warp_sum((float)((double)fwg[j] * dgam + (double)fwb[j] * dbet));
-        if (lane == 0) gsm[warp] = contrib;
-        __syncthreads();
-        if (cl == 0 && b < B) {
-          double tsum = 0.0;
-          for (int q = 0; q < PG_CH / 32; ++q) tsum += (double)gsm[bl * (PG_CH / 32) + q];
-          atomicAdd(&g_prev[b * K_prev + j], tsum);
-        }
-        __syncthreads();
+        if (lane == 0) gsm[warp][j] = contrib;
       }
+      __syncthreads();
+      if (cl < K_prev && b < B) {  // thread (cl = j, bl): the PG_CH/32 warps that share this sample slot
+        double tsum = 0.0;
+        for (int q = 0; q < PG_CH / 32; ++q) tsum += (double)gsm[bl * (PG_CH / 32) + q][cl];
+        atomicAdd(&g_prev[b * K_prev + cl], tsum);
+      }
+      __syncthreads();
     }
   }
 #pragma unroll

@@ -28,7 +28,7 @@ __global__ void film_fold_kernel(const float* __restrict__ head_w, const float* 
     for (int k = tid; k < K; k += nthr) eff_b[b * K + k] = head_b[k];
     return;
   }
-  if (tid < K_prev) cond[tid] = (float)(prev_psum[b * K_prev + tid] / n_pix);  // AdaptiveAvgPool2d(1)
+  if (tid < K_prev) cond[tid] = (float)fast_div(prev_psum[b * K_prev + tid], n_pix);  // AdaptiveAvgPool2d(1)
   __syncthreads();
   float bdot[RHSEG_KERNEL_MAX_K];
 #pragma unroll

@@ -193,15 +193,16 @@ __device__ __forceinline__ SampleLoss sample_loss(const double* __restrict__ st,
   for (int c = 0; c < RHSEG_KERNEL_MAX_K; ++c) {
     if (c < K) {
       if (sv[c][1] == 0.0) ce_nan = true;
-      else ce += -(wv[c] * sv[c][0]) / sv[c][1];
+      else ce += fast_div(-(wv[c] * sv[c][0]), sv[c][1]);
       I += wv[c] * sv[c][2];
       U += wv[c] * sv[c][3] + wv[c] * sv[c][4];
     }
   }
-  ce = ce / (double)K;
+  ce = fast_div(ce, (double)K);
   if (ce != ce) ce_nan = true;
   const double num = 2.0 * I + smooth, den = U + smooth;
-  const double dl = 1.0 - num / den;
+  const double inv_den = fast_div(1.0, den);
+  const double dl = 1.0 - num * inv_den;
   r.ce_nan = ce_nan;
   r.ce = ce_nan ? 1.0 : ce;
   r.dice_ok = !(dl != dl);
@@ -209,9 +210,9 @@ __device__ __forceinline__ SampleLoss sample_loss(const double* __restrict__ st,
 #pragma unroll
   for (int c = 0; c < RHSEG_KERNEL_MAX_K; ++c) {
     if (c < K) {
-      cf[c * 3 + 0] = ce_nan ? 0.f : (float)(-wv[c] / (sv[c][1] * (double)K * (double)B));
-      cf[c * 3 + 1] = r.dice_ok ? (float)(wv[c] * (-2.0 / den)) : 0.f;   // scaled by 1/n_valid afterwards
-      cf[c * 3 + 2] = r.dice_ok ? (float)(wv[c] * (num / (den * den))) : 0.f;
+      cf[c * 3 + 0] = ce_nan ? 0.f : (float)fast_div(-wv[c], sv[c][1] * (double)K * (double)B);
+      cf[c * 3 + 1] = r.dice_ok ? (float)(wv[c] * (-2.0 * inv_den)) : 0.f;   // scaled by 1/n_valid afterwards
+      cf[c * 3 + 2] = r.dice_ok ? (float)(wv[c] * (num * inv_den * inv_den)) : 0.f;
     }
   }
   return r;
@@ -285,7 +286,7 @@ step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ we
   __syncthreads();
   // dice coefficients carry 1/n_valid of their level
   for (int L = 0; L < nL; ++L) {
-    const float inv_nv = acc[L][2] > 0.0 ? (float)(1.0 / acc[L][2]) : 0.f;
+    const float inv_nv = acc[L][2] > 0.0 ? (float)fast_div(1.0, acc[L][2]) : 0.f;
     float* cf = coef + c_off[L];
     for (int i = tid; i < B * lv.K[L]; i += blockDim.x) {
       cf[(size_t)i * 3 + 1] *= inv_nv;
@@ -299,12 +300,12 @@ step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ we
     for (int L = 0; L < nL; ++L) {
       cons_total += cons_sm[L];  // sum over groups of mean |children - parent|
       cons_count += lv.G[L];
-      const float ce = (float)(acc[L][0] / (double)B);
-      const float dice = acc[L][2] > 0.0 ? (float)(acc[L][1] / acc[L][2]) : 0.f;
+      const float ce = (float)fast_div(acc[L][0], (double)B);
+      const float dice = acc[L][2] > 0.0 ? (float)fast_div(acc[L][1], acc[L][2]) : 0.f;
       out[2 + 4 * L] = ce; out[3 + 4 * L] = dice; out[4 + 4 * L] = (float)acc[L][2]; out[5 + 4 * L] = (float)acc[L][3];
       total += ce + dice;  // CE_L + Dice_L (0 when no sample is valid)
     }
-    const float consf = cons_count > 0 ? (float)(cons_total / (double)cons_count) : 0.f;
+    const float consf = cons_count > 0 ? (float)fast_div(cons_total, (double)cons_count) : 0.f;
     out[0] = total + consf;
     out[1] = consf;
     if (summary) {  // additive per-rank quantities for the data-parallel all-reduce (dist.py layout)
