@@ -124,25 +124,37 @@ class PeerExchange:
         from . import native
         if not (dist.is_available() and dist.is_initialized()):
             raise native.NativeError("PeerExchange needs an initialised torch.distributed process group")
+        if not torch.cuda.is_available():
+            raise native.NativeError("PeerExchange needs CUDA devices (peer memory over NVLink); there is no CPU form")
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.capacity = int(capacity)
         self._ctx = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * native.XCHG_HANDLE_BYTES)()
-        native.check(native.lib().rhseg_xchg_create(self.capacity, self.world, ctypes.byref(self._ctx), handle), "rhseg_xchg_create")
         dev = torch.device("cuda", torch.cuda.current_device())
+
+        def all_ok(rc):  # collective: every rank learns whether every rank succeeded (nobody is left waiting)
+            ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            return int(ok.item()) == 1
+
+        def fail(stage, rc):
+            if self._ctx:
+                native.lib().rhseg_xchg_destroy(self._ctx)
+            self._ctx = None
+            raise native.NativeError("%s failed on at least one rank (local status %d: %s)" % (stage, rc, native.status_string(rc)))
+
+        rc = native.lib().rhseg_xchg_create(self.capacity, self.world, ctypes.byref(self._ctx), handle)
+        if rc != 0:
+            self._ctx = None
+        if not all_ok(rc):
+            fail("rhseg_xchg_create", rc)
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
         gathered = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(gathered, mine, group=group)
         blob = bytes(torch.cat(gathered).cpu().tolist())
-        # every rank must succeed before anybody uses the buffers
         rc = native.lib().rhseg_xchg_connect(self._ctx, self.rank, blob)
-        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) != 1:
-            native.lib().rhseg_xchg_destroy(self._ctx)
-            self._ctx = None
-            raise native.NativeError("rhseg_xchg_connect failed on at least one rank (local status %d: %s)"
-                                     % (rc, native.status_string(rc)))
+        if not all_ok(rc):  # every rank must have mapped its peers before anybody uses the buffers
+            fail("rhseg_xchg_connect", rc)
 
     def all_reduce(self, summary: torch.Tensor, extra: Sequence[torch.Tensor] = (), out: torch.Tensor = None) -> torch.Tensor:
         """SUM over ranks of [summary | extra...] (fp64), written to `out` (default: a new tensor; `out` may be the
