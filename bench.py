@@ -355,6 +355,30 @@ def run_ours(args, rank, world, local_rank):
     for i, (a, b) in enumerate(conv_events):
         per_level[nL - 1 - (i % nL)].append(a.elapsed_time(b))  # backward visits the last level first
     conv_ms = [statistics.mean(v) for v in per_level]
+
+    # the same kernel on its own: back-to-back launches between ONE event pair (no event / launch gap per launch;
+    # 0.55-0.8 GB of features + gradients per launch, far beyond the 126 MB L2).  Reported beside the in-step figure.
+    dom_l = max(range(nL), key=lambda L: conv_ms[L])
+    K_dom, (hf, wf) = data["chans"][dom_l], feat_hw(wl)
+    iso = dict(dz=torch.randn(B, K_dom, hf, wf, device=dev), w=torch.randn(B, K_dom, wl["C"], device=dev),
+               df=torch.empty_like(st.feats[dom_l]), S=torch.zeros(B, K_dom, wl["C"], dtype=torch.float64, device=dev),
+               s=torch.zeros(B, K_dom, dtype=torch.float64, device=dev))
+    cur = torch.cuda.current_stream().cuda_stream
+
+    def conv_alone():
+        raw_call("rhseg_head_conv_bwd", st.feats[dom_l].data_ptr(), iso["dz"].data_ptr(), iso["w"].data_ptr(), B, wl["C"], K_dom,
+                 hf * wf, iso["df"].data_ptr(), iso["S"].data_ptr(), iso["s"].data_ptr(), 0, cur)
+    for _ in range(3):
+        conv_alone()
+    torch.cuda.synchronize()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(20):
+        conv_alone()
+    i1.record()
+    torch.cuda.synchronize()
+    conv_alone_ms = i0.elapsed_time(i1) / 20
+    del iso
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end from pinned host buffers (`e2e`) ----
@@ -434,7 +458,11 @@ def run_ours(args, rank, world, local_rank):
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "traffic": load_traffic(args.workload), "peak_source": peak_src,
                      "bytes_per_launch": alg["conv_bwd"][dom], "ms_per_launch": conv_ms[dom],
-                     "per_level_ms": conv_ms},
+                     "per_level_ms": conv_ms,
+                     "timing": "in-step: one CUDA-event pair around each launch inside eager steps (includes the launch gap the event pair opens)",
+                     "alone": {"ms_per_launch": conv_alone_ms, "achieved": alg["conv_bwd"][dom] / (conv_alone_ms * 1e-3) / 1e9,
+                               "frac": alg["conv_bwd"][dom] / (conv_alone_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                               "timing": "20 back-to-back launches of the same kernel between one event pair"}},
         "clocks": clocks,
         "e2e": {"value": world * px / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
