@@ -177,3 +177,50 @@ def test_exchange_buffer_pack_and_unpack():
     step.exchange_tail = 0
     out0 = step(feats, *params, target, fx.out_size)
     assert torch.equal(out0.summary, out.summary) and out0.exchange.numel() == out0.summary.numel()
+
+
+def test_fused_step_replays_from_a_cuda_graph():
+    """The whole step (forward, evaluation, loss, backward; side-stream fork/join included) is capturable: a replay
+    with new inputs in the same buffers gives what an eager step on those inputs gives."""
+    import rhseg_b200
+    fx = Fixture("hrnet_tl")
+    step = rhseg_b200.FusedHierStep(fx.tree, fx.level_weights)
+    mk = lambda ts: [t.to(DEV).requires_grad_(True) for t in ts]
+    feats = mk(fx.per_level("feats"))
+    params = [mk(fx.per_level("head_w")), mk(fx.per_level("head_b")), mk(fx.per_level("film_w", n=fx.nL - 1)),
+              mk(fx.per_level("film_b", n=fx.nL - 1))]
+    leaves = feats + [p for grp in params for p in grp]
+    target = torch.cat(fx.per_level("target"), dim=1).to(DEV)
+    one = torch.ones((), device=DEV)
+
+    def run():
+        out = step(feats, *params, target, fx.out_size)
+        grads = torch.autograd.grad(out.loss, leaves, grad_outputs=one)
+        return out, grads
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            run()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_out, g_grads = run()
+    gen = torch.Generator().manual_seed(5)
+    for it in range(2):
+        with torch.no_grad():
+            for f in feats:
+                f.copy_(torch.randn(f.shape, generator=gen))
+            params[0][0].mul_(0.9)
+        graph.replay()
+        torch.cuda.synchronize()
+        got = (g_out.loss.clone(), [c.clone() for c in g_out.confusion], [g.clone() for g in g_grads])
+        e_out, e_grads = run()
+        torch.cuda.synchronize()
+        close(got[0], e_out.loss, what="graph loss %d" % it)
+        for a, b in zip(got[1], e_out.confusion):
+            assert torch.equal(a, b)
+        for i, (a, b) in enumerate(zip(got[2], e_grads)):
+            close(a, b, rtol=2e-5, what="graph grad %d/%d" % (it, i))
