@@ -79,7 +79,10 @@ struct WarpConfusion {
   }
 };
 
-template <int K>
+// CT: compile-time knowledge of the level kind (-1 unknown: runtime flags; 0 root level; 1 child level without
+// consistency inputs; 2 child level with consistency) — the hot kernels instantiate the three kinds so that the
+// per-pixel code carries no flag tests.
+template <int K, int CT = -1>
 struct EvalAccum {
   static constexpr int NS = RHSEG_NSTAT;
   static constexpr int NACC = K * NS + K;  // statistics + one consistency accumulator per group-start channel
@@ -88,6 +91,8 @@ struct EvalAccum {
   LevelInfo li;
   int child, nc;
   bool do_cons;
+  __device__ __forceinline__ bool is_child() const { return CT < 0 ? child != 0 : CT >= 1; }
+  __device__ __forceinline__ bool has_cons() const { return CT < 0 ? do_cons : CT == 2; }
 
   // hist: shared int[(K+1)^2], zeroed here (contains a __syncthreads)
   __device__ __forceinline__ void init(int child_, bool do_cons_, const int32_t* table, int* hist, int nthreads) {
@@ -122,7 +127,7 @@ struct EvalAccum {
       for (int v = 0; v < VEC; ++v) { tv.v[v] = -1.f; ptv[k][v] = -1.f; }
       if (ok) {
         tv = ld_cached<VEC>(targets + (size_t)b * t_bs + (size_t)k * t_cs + px);
-        if (do_cons && ((li.start_mask >> k) & 1)) {
+        if (has_cons() && ((li.start_mask >> k) & 1)) {
           const Vec<VEC> pv = ld_cached<VEC>(parent_targets + (size_t)b * pt_bs + (size_t)li.parent[k] * pt_cs + px);
 #pragma unroll
           for (int v = 0; v < VEC; ++v) ptv[k][v] = pv.v[v];
@@ -131,7 +136,7 @@ struct EvalAccum {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) t[k][v] = tv.v[v];
     }
-    if (ok && do_cons) {
+    if (ok && has_cons()) {
       if constexpr (VEC == 4) {
         const uchar4 q = *reinterpret_cast<const uchar4*>(prev_idx + (size_t)b * N + px);
         pidx[0] = q.x; pidx[1] = q.y; pidx[2] = q.z; pidx[3] = q.w;
@@ -186,12 +191,12 @@ struct EvalAccum {
       float pm = 0.f;
 #pragma unroll
       for (int k = 0; k < K; ++k) pm += pr[k];
-      const int pc = pm != 0.f ? (child ? idx + 1 : idx) : 0;
-      int tc = process_class<K>(et, child != 0);
-      if (!ok || (child && tc == 0)) tc = -1;  // out of range / torchmetrics ignore_index=0 on child levels
+      const int pc = pm != 0.f ? (is_child() ? idx + 1 : idx) : 0;
+      int tc = process_class<K>(et, is_child());
+      if (!ok || (is_child() && tc == 0)) tc = -1;  // out of range / torchmetrics ignore_index=0 on child levels
       wc.add(tc, pc);
     }
-    if (do_cons && ok) {
+    if (has_cons() && ok) {
       float gs[K];
       group_sum<K>(pr, li.start_mask, gs);  // children one-hots summed per group
 #pragma unroll
@@ -226,7 +231,7 @@ struct EvalAccum {
 #pragma unroll
       for (int w = 0; w < NWARP; ++w) acc += (double)red[w * NACC + tid];
       if (tid < K * NS) atomicAdd(&stats[(size_t)b * K * NS + tid], acc);
-      else if (do_cons && ((li.start_mask >> (tid - K * NS)) & 1)) atomicAdd(&cons[table[RHSEG_TBL_GROUP_OF + tid - K * NS]], acc);
+      else if (has_cons() && ((li.start_mask >> (tid - K * NS)) & 1)) atomicAdd(&cons[table[RHSEG_TBL_GROUP_OF + tid - K * NS]], acc);
     }
     for (int i = tid; i < nc * nc; i += NWARP * 32)
       if (hist[i]) atomicAdd(&conf[i], (unsigned long long)hist[i]);

@@ -151,7 +151,7 @@ __global__ void metric_ratios_kernel(const long long* __restrict__ conf, int nc,
 // so neither the one-hot tensors nor the eval targets are ever materialised.
 // out layout (8-byte words): [B*K*5 fp64 stats][RHSEG_MAX_K fp64 consistency sums][nc*nc int64 confusion]
 // ------------------------------------------------------------------------------------
-template <int K, int VEC, int MINB, int THREADS>
+template <int K, int VEC, int MINB, int THREADS, int CT = -1>
 __global__ void __launch_bounds__(THREADS, MINB)
 level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ targets, long t_bstride, long t_cstride,
                   const float* __restrict__ parent_targets, long pt_bstride, long pt_cstride,
@@ -162,7 +162,7 @@ level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ ta
   __shared__ float red[THREADS / 32][EvalAccum<K>::NACC];
   __shared__ int hist[(K + 1) * (K + 1)];
   const int b = blockIdx.y, tid = threadIdx.x;
-  EvalAccum<K> ev;
+  EvalAccum<K, CT> ev;
   ev.init(child, child && prev_idx != nullptr && parent_targets != nullptr, table, hist, THREADS);
   const float* zb = logits + (size_t)b * K * N;
   // persistent over the sample's pixel vectors: one resident wave, statistics reduced once per CTA
@@ -346,9 +346,22 @@ extern "C" int rhseg_level_eval(const float* logits, const float* targets, long 
       if (tune == 1)
         launch_pdl(level_eval_kernel<KK, 4, 3, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
             pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
-      else
+      else if (getenv("RHSEG_NO_CT_EVAL"))
         launch_pdl(level_eval_kernel<KK, 4, 2, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
             pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
+      else {
+        // level kind known at launch: three instantiations without flag tests in the per-pixel code
+        const int ct = !child ? 0 : ((prev_idx != nullptr && parent_targets != nullptr) ? 2 : 1);
+        if (ct == 0)
+          launch_pdl(level_eval_kernel<KK, 4, 2, THREADS, 0>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
+              pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
+        else if (ct == 1)
+          launch_pdl(level_eval_kernel<KK, 4, 2, THREADS, 1>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
+              pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
+        else
+          launch_pdl(level_eval_kernel<KK, 4, 2, THREADS, 2>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
+              pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
+      }
     } else {
       dim3 grid((unsigned)balanced_grid((N + THREADS - 1) / THREADS, slots), B);
       launch_pdl(level_eval_kernel<KK, 1, 2, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
