@@ -368,16 +368,18 @@ def run_ours(args, rank, world, local_rank):
     def conv_alone():
         raw_call("rhseg_head_conv_bwd", st.feats[dom_l].data_ptr(), iso["dz"].data_ptr(), iso["w"].data_ptr(), B, wl["C"], K_dom,
                  hf * wf, iso["df"].data_ptr(), iso["S"].data_ptr(), iso["s"].data_ptr(), 0, cur)
-    for _ in range(3):
-        conv_alone()
-    torch.cuda.synchronize()
-    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    i0.record()
-    for _ in range(20):
-        conv_alone()
-    i1.record()
-    torch.cuda.synchronize()
-    conv_alone_ms = i0.elapsed_time(i1) / 20
+    conv_alone_ms = float("nan")
+    if not args.no_alone:
+        for _ in range(3):
+            conv_alone()
+        torch.cuda.synchronize()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        for _ in range(20):
+            conv_alone()
+        i1.record()
+        torch.cuda.synchronize()
+        conv_alone_ms = i0.elapsed_time(i1) / 20
     del iso
     clocks = sampler.stop() if rank == 0 else None
 
@@ -560,6 +562,7 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropin", action="store_true", help="skip timing the drop-in module path (profiling runs)")
+    ap.add_argument("--no-alone", action="store_true", help="skip the back-to-back timing of the dominant kernel (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
