@@ -487,13 +487,17 @@ struct EvalArgs {
   unsigned char* idx_out;
 };
 
-template <int K, int VEC, int MODE, bool EVAL>
+// EVALK: 0 = no evaluation, 1 = evaluate (no consistency inputs), 2 = evaluate with the consistency sums; together
+// with MODE this fixes the level kind at compile time (EvalAccum's CT).
+template <int K, int VEC, int MODE, int EVALK>
 __global__ void __launch_bounds__(256, VEC == 2 ? 3 : 2)
 upsample_act_tiled_kernel(const float* __restrict__ z_lo, const float* __restrict__ prev_probs,
                           const int32_t* __restrict__ table, int Hf, int Wf, int H, int W, int K_prev, float sy,
                           float sx, int tiles_x, int tiles_per_sample, float* __restrict__ logits,
                           float* __restrict__ probs, double* __restrict__ psum, EvalArgs ea) {
   pdl_wait();
+  constexpr bool EVAL = EVALK != 0;
+  constexpr int CT = MODE == RHSEG_ACT_SIGMOID ? 0 : (EVALK == 2 ? 2 : 1);
   constexpr int TH = 16, TW = 16 * VEC;
   constexpr int PH = TH + 2, PW = TW + 2;  // patch bound for scale <= 1
   // double buffered when it fits the static limit: the next tile's patch streams in (cp.async) while this one is used
@@ -503,7 +507,7 @@ upsample_act_tiled_kernel(const float* __restrict__ z_lo, const float* __restric
   __shared__ float ered[EVAL ? 8 * EvalAccum<K>::NACC : 1];
   __shared__ int hist[EVAL ? (K + 1) * (K + 1) : 1];
   const int b = blockIdx.y, tid = threadIdx.x;
-  EvalAccum<K> ev;
+  EvalAccum<K, CT> ev;
   if constexpr (EVAL)
     ev.init(ea.child, ea.child && ea.prev_idx != nullptr && ea.parent_targets != nullptr, table, hist, 256);
   const LevelInfo li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? table : nullptr);
@@ -693,8 +697,11 @@ static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32
       const int slots2 = std::max(1, device_sm_count() * 3 / B);
       const int tiles_x = (W + 31) / 32, tiles = tiles_x * ((H + 15) / 16);
       dim3 grid(balanced_grid(tiles, slots2), B);
-      if (ea) launch_pdl(upsample_act_tiled_kernel<K, 2, MODE, true>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
-      else launch_pdl(upsample_act_tiled_kernel<K, 2, MODE, false>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
+      if (ea) {
+        if (ea->prev_idx && ea->parent_targets && ea->child) launch_pdl(upsample_act_tiled_kernel<K, 2, MODE, 2>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
+        else launch_pdl(upsample_act_tiled_kernel<K, 2, MODE, 1>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
+      }
+      else launch_pdl(upsample_act_tiled_kernel<K, 2, MODE, 0>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
       RHSEG_LAUNCH_CHECK();
       return RHSEG_OK;
     }
@@ -702,13 +709,19 @@ static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32
     if (v4) {
       const int tiles_x = (W + 63) / 64, tiles = tiles_x * ((H + 15) / 16);
       dim3 grid(balanced_grid(tiles, slots), B);
-      if (ea) launch_pdl(upsample_act_tiled_kernel<K, 4, MODE, true>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
-      else launch_pdl(upsample_act_tiled_kernel<K, 4, MODE, false>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
+      if (ea) {
+        if (ea->prev_idx && ea->parent_targets && ea->child) launch_pdl(upsample_act_tiled_kernel<K, 4, MODE, 2>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
+        else launch_pdl(upsample_act_tiled_kernel<K, 4, MODE, 1>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
+      }
+      else launch_pdl(upsample_act_tiled_kernel<K, 4, MODE, 0>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
     } else {
       const int tiles_x = (W + 15) / 16, tiles = tiles_x * ((H + 15) / 16);
       dim3 grid(balanced_grid(tiles, slots), B);
-      if (ea) launch_pdl(upsample_act_tiled_kernel<K, 1, MODE, true>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
-      else launch_pdl(upsample_act_tiled_kernel<K, 1, MODE, false>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
+      if (ea) {
+        if (ea->prev_idx && ea->parent_targets && ea->child) launch_pdl(upsample_act_tiled_kernel<K, 1, MODE, 2>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
+        else launch_pdl(upsample_act_tiled_kernel<K, 1, MODE, 1>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, *ea);
+      }
+      else launch_pdl(upsample_act_tiled_kernel<K, 1, MODE, 0>, dim3(grid), dim3(256), 0, st, z_lo, prev_probs, table, Hf, Wf, H, W, K_prev, sy, sx, tiles_x, tiles, logits, probs, psum, none);
     }
     RHSEG_LAUNCH_CHECK();
     return RHSEG_OK;
