@@ -198,8 +198,10 @@ constexpr int XR_MAXROWS = 8, XR_THREADS = 256, XR_MAXW = 12;
 // feeds rows i0(y), i1(y) with the forward's own lerp weights) and the accumulator is added into a
 // PRE-ZEROED dz_lo at the end.  band >= taps per low-res row, so a low-res row receives from at most two
 // CTAs and the two-term fp32 sum is order independent: deterministic, no tmpx tensor, no second kernel.
-template <int K, int SRC, int MODE, bool BAND = false>
-__global__ void __launch_bounds__(XR_THREADS)
+// NOACT: the caller knows that no gradient reaches this level's probabilities (last level of the tree): the
+// activation-backward code is compiled out.
+template <int K, int SRC, int MODE, bool BAND = false, bool NOACT = false, int THREADS = XR_THREADS>
+__global__ void __launch_bounds__(THREADS)
 dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, int H, int W, float sx, int XR_ROWS,
                        float* __restrict__ tmpx, int Hf, float sy, int band, int acc_rows, float* __restrict__ dz_lo) {
   pdl_wait();
@@ -216,9 +218,9 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
   const int band_y1 = BAND ? min(H, band_y0 + band) : H;
   const int i_lo = BAND ? make_lerp(band_y0, sy, Hf).i0 : 0;
   if constexpr (BAND)
-    for (int e = tid; e < K * acc_rows * Wf; e += XR_THREADS) accs[e] = 0.f;
+    for (int e = tid; e < K * acc_rows * Wf; e += THREADS) accs[e] = 0.f;
 
-  for (int j = tid; j < Wf; j += XR_THREADS) {
+  for (int j = tid; j < Wf; j += THREADS) {
     int lo, hi;
     lerp_support(j, sx, W, lo, hi);
     int first = -1, cnt = 0;
@@ -241,7 +243,7 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
   __syncthreads();  // tables ready / previous block's readers done
   // ---- phase 1: gradient of ROWS full rows -> shared memory (4 pixels per thread and step) ----
   if constexpr (SRC == 0) {
-    for (int e = tid; e < rows * vec_per_row; e += XR_THREADS) {
+    for (int e = tid; e < rows * vec_per_row; e += THREADS) {
       const int r = e / vec_per_row, xv = (e - r * vec_per_row) * 4;
       const size_t px = (size_t)(y0 + r) * W + xv;
 #pragma unroll
@@ -262,8 +264,8 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
       Cc[k] = gdi * __ldg(cf + 2);
       gu[k] = fa.g_uniform ? (float)fa.g_uniform[b * K + k] * fa.inv_npix : 0.f;
     }
-    const bool has_act = MODE != RHSEG_ACT_ZEROS && (fa.g_uniform != nullptr || (fa.dp_pix != nullptr && fa.pix_mask != 0));
-    for (int e = tid; e < rows * vec_per_row; e += XR_THREADS) {
+    const bool has_act = !NOACT && MODE != RHSEG_ACT_ZEROS && (fa.g_uniform != nullptr || (fa.dp_pix != nullptr && fa.pix_mask != 0));
+    for (int e = tid; e < rows * vec_per_row; e += THREADS) {
       const int r = e / vec_per_row, xv = (e - r * vec_per_row) * 4;
       const size_t px = (size_t)(y0 + r) * W + xv;
       float z[K][4], t[K][4], ex[K][4], pp[K][4], o[K][4], dpar[K][4];
@@ -325,7 +327,7 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
   // ---- phase 2: reduce along x: tmpx[b][k][y][j] = sum_x wx(x, j) dz[k][y][x] ----
   if constexpr (BAND) {
     // thread <-> (k, j) column: it alone touches accs[k][*][j]
-    for (int e = tid; e < K * Wf; e += XR_THREADS) {
+    for (int e = tid; e < K * Wf; e += THREADS) {
       const int k = e / Wf, j = e - k * Wf;
       const float* wt = wtab + j * XR_MAXW;
       const int n = wcnt[j], ws = wstart[j];
@@ -340,7 +342,7 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
       }
     }
   } else
-  for (int e = tid; e < K * rows * Wf; e += XR_THREADS) {
+  for (int e = tid; e < K * rows * Wf; e += THREADS) {
     const int j = e % Wf;
     const int kr = e / Wf;
     const int r = kr % rows, k = kr / rows;
@@ -356,7 +358,7 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
     __syncthreads();
     const int i_hi = make_lerp(band_y1 - 1, sy, Hf).i1;
     const int nrow = i_hi - i_lo + 1;
-    for (int e = tid; e < K * nrow * Wf; e += XR_THREADS) {
+    for (int e = tid; e < K * nrow * Wf; e += THREADS) {
       const int j = e % Wf;
       const int kr = e / Wf;
       const int ri = kr % nrow, k = kr / nrow;
@@ -487,17 +489,21 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
     const bool no_band = getenv("RHSEG_NO_BAND_ADJOINT") != nullptr;
     if (rows_ok && prezeroed && !no_band && sy > 0.f && sy <= 1.0f) {
       // band kernel: x- and y-reduction in one pass into the pre-zeroed dz_lo
-      auto kern = dz_rows_xreduce_kernel<K, SRC, MODE, true>;
+      // without the activation backward the kernel needs 64 registers: 512-thread CTAs double the warps per SM
+      const bool no_act = SRC == 1 && (MODE == RHSEG_ACT_ZEROS || (fa.g_uniform == nullptr && (fa.dp_pix == nullptr || fa.pix_mask == 0)));
+      const int nthreads = no_act ? 2 * XR_THREADS : XR_THREADS;
+      auto kern = no_act ? dz_rows_xreduce_kernel<K, SRC, MODE, true, (SRC == 1), ((SRC == 1) ? 2 * XR_THREADS : XR_THREADS)>
+                         : dz_rows_xreduce_kernel<K, SRC, MODE, true, false, XR_THREADS>;
       // >= taps per low-res row (ceil(2/sy) - 1 would do): at most two CTAs feed one low-res row
       const int min_band = std::max(2, (int)ceilf(2.0f / sy));
       // rows per phase-1 pass: the one that wastes the fewest threads (a pass handles rows * W/4 four-pixel items
-      // with XR_THREADS threads: 2 rows of 620 px keep only 60 % of them busy, 3 rows 91 %)
+      // with nthreads threads: 2 rows of 620 px keep only 60 % of them busy, 3 rows 91 %)
       const int vpr = W / 4;
       int sub = 1;
       double best_util = 0.0;
       for (int r = 1; r <= 4; ++r) {
         const int items = r * vpr;
-        const double util = (double)items / (double)(((items + XR_THREADS - 1) / XR_THREADS) * XR_THREADS);
+        const double util = (double)items / (double)(((items + nthreads - 1) / nthreads) * nthreads);
         if (util > best_util + 1e-9) { best_util = util; sub = r; }
       }
       auto smem_for = [&](int band) {
@@ -509,7 +515,7 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
       const size_t smem0 = smem_for(round_band(min_band));
       if (smem0 <= 200 * 1024) {
         if (smem0 > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-        RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, XR_THREADS, smem0));
+        RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem0));
       }
       if (per_sm >= 1) {
         const long slots = std::max<long>(1, (long)per_sm * device_sm_count() / B);
@@ -519,7 +525,7 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
         if (smem_b <= 200 * 1024) {
           if (smem_b > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
           dim3 grid((unsigned)((H + band - 1) / band), B);
-          launch_pdl(kern, dim3(grid), dim3(XR_THREADS), smem_b, st, dz_hi, fa, Wf, H, W, sx, sub, (float*)nullptr, Hf, sy, band,
+          launch_pdl(kern, dim3(grid), dim3(nthreads), smem_b, st, dz_hi, fa, Wf, H, W, sx, sub, (float*)nullptr, Hf, sy, band,
                      acc_rows, dz_lo);
           RHSEG_LAUNCH_CHECK();
           return RHSEG_OK;
