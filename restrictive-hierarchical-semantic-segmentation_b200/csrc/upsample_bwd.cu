@@ -198,10 +198,12 @@ constexpr int XR_MAXROWS = 8, XR_THREADS = 256, XR_MAXW = 12;
 // feeds rows i0(y), i1(y) with the forward's own lerp weights) and the accumulator is added into a
 // PRE-ZEROED dz_lo at the end.  band >= taps per low-res row, so a low-res row receives from at most two
 // CTAs and the two-term fp32 sum is order independent: deterministic, no tmpx tensor, no second kernel.
-// NOACT: the caller knows that no gradient reaches this level's probabilities (last level of the tree): the
-// activation-backward code is compiled out.
-template <int K, int SRC, int MODE, bool BAND = false, bool NOACT = false, int THREADS = XR_THREADS>
-__global__ void __launch_bounds__(THREADS)
+// ACTK: what the launcher knows about the gradient reaching this level's probabilities: 0 = decide at run time,
+// 1 = none (last level of the tree: the activation backward is compiled out), 2 = sigmoid level that only receives
+// the uniform FiLM-pool gradient (level 0 of a two-level tree: no per-pixel term, nothing to hand to a parent).
+// Kinds 1 and 2 fit 64 registers and run 512-thread CTAs (twice the warps per SM).
+template <int K, int SRC, int MODE, bool BAND = false, int ACTK = 0, int THREADS = XR_THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
 dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, int H, int W, float sx, int XR_ROWS,
                        float* __restrict__ tmpx, int Hf, float sy, int band, int acc_rows, float* __restrict__ dz_lo) {
   pdl_wait();
@@ -264,7 +266,9 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
       Cc[k] = gdi * __ldg(cf + 2);
       gu[k] = fa.g_uniform ? (float)fa.g_uniform[b * K + k] * fa.inv_npix : 0.f;
     }
-    const bool has_act = !NOACT && MODE != RHSEG_ACT_ZEROS && (fa.g_uniform != nullptr || (fa.dp_pix != nullptr && fa.pix_mask != 0));
+    constexpr bool NOACT = ACTK == 1, UNIF = ACTK == 2;
+    static_assert(!UNIF || MODE == RHSEG_ACT_SIGMOID, "uniform-only kind: sigmoid levels");
+    const bool has_act = UNIF || (!NOACT && MODE != RHSEG_ACT_ZEROS && (fa.g_uniform != nullptr || (fa.dp_pix != nullptr && fa.pix_mask != 0)));
     for (int e = tid; e < rows * vec_per_row; e += THREADS) {
       const int r = e / vec_per_row, xv = (e - r * vec_per_row) * 4;
       const size_t px = (size_t)(y0 + r) * W + xv;
@@ -276,7 +280,7 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
         Vec<4> ev;
 #pragma unroll
         for (int v = 0; v < 4; ++v) ev.v[v] = 0.f;
-        if (has_act && fa.dp_pix && ((fa.pix_mask >> k) & 1u)) ev = ld_stream<4>(fa.dp_pix + ((size_t)b * K + k) * N + px);
+        if (!UNIF && has_act && fa.dp_pix && ((fa.pix_mask >> k) & 1u)) ev = ld_stream<4>(fa.dp_pix + ((size_t)b * K + k) * N + px);
 #pragma unroll
         for (int v = 0; v < 4; ++v) { z[k][v] = zv.v[v]; t[k][v] = tv.v[v]; ex[k][v] = ev.v[v]; pp[k][v] = 0.f; }
       }
@@ -490,10 +494,15 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int 
     if (rows_ok && prezeroed && !no_band && sy > 0.f && sy <= 1.0f) {
       // band kernel: x- and y-reduction in one pass into the pre-zeroed dz_lo
       // without the activation backward the kernel needs 64 registers: 512-thread CTAs double the warps per SM
-      const bool no_act = SRC == 1 && (MODE == RHSEG_ACT_ZEROS || (fa.g_uniform == nullptr && (fa.dp_pix == nullptr || fa.pix_mask == 0)));
-      const int nthreads = no_act ? 2 * XR_THREADS : XR_THREADS;
-      auto kern = no_act ? dz_rows_xreduce_kernel<K, SRC, MODE, true, (SRC == 1), ((SRC == 1) ? 2 * XR_THREADS : XR_THREADS)>
-                         : dz_rows_xreduce_kernel<K, SRC, MODE, true, false, XR_THREADS>;
+      const bool no_pix = fa.dp_pix == nullptr || fa.pix_mask == 0;
+      const bool no_act = SRC == 1 && (MODE == RHSEG_ACT_ZEROS || (fa.g_uniform == nullptr && no_pix));
+      const bool unif = SRC == 1 && MODE == RHSEG_ACT_SIGMOID && fa.g_uniform != nullptr && no_pix;
+      const int nthreads = (no_act || unif) ? 2 * XR_THREADS : XR_THREADS;
+      constexpr int T2 = (SRC == 1) ? 2 * XR_THREADS : XR_THREADS;
+      auto kern = no_act ? dz_rows_xreduce_kernel<K, SRC, MODE, true, (SRC == 1 ? 1 : 0), T2>
+                : unif   ? dz_rows_xreduce_kernel<K, SRC, MODE, true, ((SRC == 1 && MODE == RHSEG_ACT_SIGMOID) ? 2 : 0),
+                                                  ((SRC == 1 && MODE == RHSEG_ACT_SIGMOID) ? T2 : XR_THREADS)>
+                         : dz_rows_xreduce_kernel<K, SRC, MODE, true, 0, XR_THREADS>;
       // >= taps per low-res row (ceil(2/sy) - 1 would do): at most two CTAs feed one low-res row
       const int min_band = std::max(2, (int)ceilf(2.0f / sy));
       // rows per phase-1 pass: the one that wastes the fewest threads (a pass handles rows * W/4 four-pixel items
