@@ -37,6 +37,12 @@ extern "C" {
 #define RHSEG_MAX_LEVELS 8       /* tree depth rhseg_step_finalize handles in one launch  */
 #define RHSEG_STITCH_MAX_LEAVES 16 /* leaf channels of a flat model rhseg_stitch_levels reads */
 #define RHSEG_STITCH_MAX_OUT 32    /* tree nodes (output channels) it writes                 */
+/* Optional hint OR-ed into the `act_mode` (grouped levels) and `child` arguments: every parent group of the
+ * level has exactly `gsz` channels (the reference's trees: one group of 4, 2 or 3; two groups of 2).  The kernels
+ * then run code with the group layout fixed at compile time; 0 (no hint) reads the layout from the level table.
+ * A hint that contradicts the table gives wrong results: pass what rhseg_tree_compile_level's table says.   */
+#define RHSEG_GROUP_HINT(gsz) ((int)(gsz) << 8)
+#define RHSEG_GROUP_HINT_OF(arg) (((arg) >> 8) & 0xff)
 
 enum {
   RHSEG_OK = 0,

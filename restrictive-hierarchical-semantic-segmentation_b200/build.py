@@ -59,8 +59,25 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
     srcs = _sources()
 
+    headers = hashlib.sha256()
+    for root in (CSRC, INCLUDE):
+        for f in sorted(os.listdir(root)):
+            if f.endswith((".cuh", ".h")):
+                with open(os.path.join(root, f), "rb") as fh:
+                    headers.update(f.encode() + fh.read())
+    headers.update(" ".join(NVCC_FLAGS).encode())
+
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        # per-object stamp (source + every header + flags): unchanged translation units are not recompiled
+        h = headers.copy()
+        with open(os.path.join(CSRC, src), "rb") as fh:
+            h.update(fh.read())
+        stamp = obj + ".sha256"
+        if not force and not verbose and os.path.exists(obj) and os.path.exists(stamp):
+            with open(stamp) as fh:
+                if fh.read().strip() == h.hexdigest():
+                    return obj
         cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -69,6 +86,8 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
         if verbose:
             sys.stderr.write(r.stderr)
+        with open(stamp, "w") as fh:
+            fh.write(h.hexdigest())
         return obj
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:

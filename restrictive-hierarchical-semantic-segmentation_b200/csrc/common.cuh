@@ -204,7 +204,20 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ float sigmoidf_ref(float z) { return rcp_approx(1.0f + __expf(-z)); }
+// exp / log on the SFU without the denormal fix-up code __expf / __logf carry (4-5 instructions each): the
+// probability math only sees exp(x <= 0) -- results below 2^-126 flush to zero -- and log(sum >= 1).
+__device__ __forceinline__ float exp_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+__device__ __forceinline__ float log_fast(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.6931471805599453f;
+}
+// 1 / (1 + exp(-z)); exp(-z) overflows to +inf for z < -88.7 and the reciprocal is then 0, as in the exact formula
+__device__ __forceinline__ float sigmoidf_ref(float z) { return rcp_approx(1.0f + exp_fast(-z)); }
 
 // x / y for the tiny latency-bound kernels (finalize, parameter gradients): fp32 reciprocal seed + two Newton steps
 // in fp64 (~1 ulp) instead of the ~40-instruction IEEE division routine on the critical thread.  y == 0 gives NaN
@@ -227,7 +240,7 @@ __device__ __forceinline__ void grouped_softmax(const float (&z)[K], int start_m
   for (int k = K - 2; k >= 0; --k) m[k] = ((start_mask >> (k + 1)) & 1) ? m[k] : m[k + 1];
   float e[K], s[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) e[k] = __expf(z[k] - m[k]);
+  for (int k = 0; k < K; ++k) e[k] = exp_fast(z[k] - m[k]);
   s[0] = e[0];
 #pragma unroll
   for (int k = 1; k < K; ++k) s[k] = ((start_mask >> k) & 1) ? e[k] : s[k - 1] + e[k];
@@ -273,7 +286,7 @@ __device__ __forceinline__ void fast_softmax(const float (&z)[K], float (&p)[K],
   for (int k = 1; k < K; ++k) mx = fmaxf(mx, z[k]);
   sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < K; ++k) { p[k] = __expf(z[k] - mx); sum += p[k]; }
+  for (int k = 0; k < K; ++k) { p[k] = exp_fast(z[k] - mx); sum += p[k]; }
   const float inv = rcp_approx(sum);
 #pragma unroll
   for (int k = 0; k < K; ++k) p[k] *= inv;

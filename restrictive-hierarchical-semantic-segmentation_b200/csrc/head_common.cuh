@@ -21,10 +21,12 @@ struct EvalArgs {
   unsigned char* idx_out;
 };
 
-// hi-res pass of an upsampled head (head_up.cu): K / activation mode dispatch included
-int fwd_upsampled_dispatch(int K, int act_mode, const float* z_lo, const float* prev_probs, const int32_t* table, int B,
+// hi-res pass of an upsampled head (head_up.cu): K / activation mode dispatch included.  act_arg = activation mode |
+// RHSEG_GROUP_HINT.  *need_eval is set when `ea` was given but the shape took the generic kernel, which does not
+// evaluate: the caller then runs rhseg_level_eval on the logits.
+int fwd_upsampled_dispatch(int K, int act_arg, const float* z_lo, const float* prev_probs, const int32_t* table, int B,
                            int Hf, int Wf, int H, int W, int K_prev, float* logits, float* probs, double* psum,
-                           cudaStream_t st, const EvalArgs* ea);
+                           cudaStream_t st, const EvalArgs* ea, bool* need_eval);
 
 // ------------------------------------------------------------------------------------
 // Activation epilogue shared by the fused and the upsampled path.  P pixels per thread.

@@ -418,8 +418,10 @@ extern "C" int rhseg_film_fold(const float* head_w, const float* head_b, const f
 
 static int level_fwd_impl(const float* feats, const float* eff_w, const float* eff_b,
                           const float* prev_probs, const int32_t* table, int B, int C, int Hf, int Wf,
-                          int H, int W, int K, int K_prev, int act_mode, float* z_lo, float* logits,
-                          float* probs, double* psum, int zero_psum, void* stream, const EvalArgs* ea) {
+                          int H, int W, int K, int K_prev, int act_arg, float* z_lo, float* logits,
+                          float* probs, double* psum, int zero_psum, void* stream, const EvalArgs* ea, bool* need_eval) {
+  const int act_mode = act_arg & 0xff;
+  if (need_eval) *need_eval = false;
   if (!feats || !eff_w || !eff_b || !logits || !probs || !psum) return RHSEG_ERR_ARG;
   if (B <= 0 || C <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
@@ -430,6 +432,7 @@ static int level_fwd_impl(const float* feats, const float* eff_w, const float* e
   const bool zlo_zeroed = (zero_psum & 2) != 0;
   const bool up = (H != Hf) || (W != Wf);
   if (ea && !up) return RHSEG_ERR_UNSUPPORTED;
+  if (act_mode == RHSEG_ACT_GROUPED && table == nullptr) return RHSEG_ERR_ARG;
   const int Nf = Hf * Wf;
   if (!up) {
     RHSEG_DISPATCH_K(K, {
@@ -459,7 +462,10 @@ static int level_fwd_impl(const float* feats, const float* eff_w, const float* e
     }
     if (rc != RHSEG_OK) return rc;
   });
-  return fwd_upsampled_dispatch(K, act_mode, z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, logits, probs, psum, st, ea);
+  bool ne = false;
+  const int rc = fwd_upsampled_dispatch(K, act_arg, z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, logits, probs, psum, st, ea, &ne);
+  if (need_eval) *need_eval = ne;
+  return rc;
 }
 
 extern "C" int rhseg_head_level_fwd(const float* feats, const float* eff_w, const float* eff_b,
@@ -467,7 +473,7 @@ extern "C" int rhseg_head_level_fwd(const float* feats, const float* eff_w, cons
                                     int H, int W, int K, int K_prev, int act_mode, float* z_lo, float* logits,
                                     float* probs, double* psum, int zero_psum, void* stream) {
   return level_fwd_impl(feats, eff_w, eff_b, prev_probs, table, B, C, Hf, Wf, H, W, K, K_prev, act_mode, z_lo, logits, probs,
-                        psum, zero_psum, stream, nullptr);
+                        psum, zero_psum, stream, nullptr, nullptr);
 }
 
 extern "C" int rhseg_head_level_fwd_eval(const float* feats, const float* eff_w, const float* eff_b,
@@ -479,7 +485,7 @@ extern "C" int rhseg_head_level_fwd_eval(const float* feats, const float* eff_w,
                                          int flags, void* stream) {
   if (!targets || !out_words) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
-  const int child = act_mode == RHSEG_ACT_SIGMOID ? 0 : 1;
+  const int child = (act_mode & 0xff) == RHSEG_ACT_SIGMOID ? 0 : 1;
   const int nc = child ? K + 1 : K;
   const size_t words = (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K + (size_t)nc * nc;
   if (!(flags & RHSEG_EVAL_PREZEROED)) RHSEG_CUDA(cudaMemsetAsync(out_words, 0, words * 8, (cudaStream_t)stream));
@@ -487,6 +493,12 @@ extern "C" int rhseg_head_level_fwd_eval(const float* feats, const float* eff_w,
   double* cons = stats + (size_t)B * K * RHSEG_NSTAT;
   EvalArgs ea{targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, child, stats, cons,
               reinterpret_cast<unsigned long long*>(cons + RHSEG_MAX_K), idx_out};
-  return level_fwd_impl(feats, eff_w, eff_b, prev_probs, table, B, C, Hf, Wf, H, W, K, K_prev, act_mode, z_lo, logits, probs,
-                        psum, (flags & 2), stream, &ea);
+  bool need_eval = false;
+  const int rc = level_fwd_impl(feats, eff_w, eff_b, prev_probs, table, B, C, Hf, Wf, H, W, K, K_prev, act_mode, z_lo, logits,
+                                probs, psum, (flags & 2), stream, &ea, &need_eval);
+  if (rc != RHSEG_OK || !need_eval) return rc;
+  // shapes the band kernel does not take: the evaluation runs as its own kernel on the finished logits
+  return rhseg_level_eval(logits, targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, table, B, K,
+                          H * W, child | RHSEG_GROUP_HINT(RHSEG_GROUP_HINT_OF(act_mode)), out_words, idx_out,
+                          RHSEG_EVAL_PREZEROED, stream);
 }

@@ -3,8 +3,10 @@
 // (train.py:206-231, predictEval.py:409-422).
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "eval_accum.cuh"
+#include "hires.cuh"
 
 namespace rhseg {
 
@@ -195,6 +197,174 @@ level_eval_kernel(const float* __restrict__ logits, const float* __restrict__ ta
 }
 
 // ------------------------------------------------------------------------------------
+// The same evaluation as a bulk-copy pipeline (the fast path: 16-byte aligned planes, N % 16 == 0).
+// The flattened (sample, pixel) range is split EVENLY over one resident wave of CTAs in units of 16 pixels.  A
+// producer warp streams stages of up to EVP_PX consecutive pixels of one sample -- K logit planes, K target
+// planes and, for the consistency term, the parent's target plane per group and the previous level's index map --
+// into a shared-memory ring with 1-D bulk async copies; eight consumer warps read only shared memory, so no
+// global-load latency is exposed and the per-pixel code (hires.cuh: EvalAcc) is all that is left.
+// ------------------------------------------------------------------------------------
+constexpr int EVP_CW = 8, EVP_CONSUMERS = EVP_CW * 32, EVP_THREADS = EVP_CONSUMERS + 32, EVP_PX = EVP_CONSUMERS * 4;
+
+template <int K, int CT, int GSZ>
+__host__ __device__ constexpr int evp_stage_bytes() {
+  return (2 * K + (CT == 2 ? Groups<K, GSZ>::NG : 0)) * EVP_PX * 4 + (CT == 2 ? EVP_PX : 0);
+}
+
+template <int K, int CT, int GSZ>
+__global__ void __launch_bounds__(EVP_THREADS)
+level_eval_pipe_kernel(const float* __restrict__ logits, const float* __restrict__ targets, long t_bstride, long t_cstride,
+                       const float* __restrict__ parent_targets, long pt_bstride, long pt_cstride,
+                       const unsigned char* __restrict__ prev_idx, const int32_t* __restrict__ table, long N,
+                       long units_total, int ns, double* __restrict__ stats, double* __restrict__ cons,
+                       unsigned long long* __restrict__ conf, unsigned char* __restrict__ idx_out) {
+  using Acc = EvalAcc<K, CT, GSZ>;
+  constexpr bool CONS = CT == 2;
+  constexpr int NG = Groups<K, GSZ>::NG;
+  constexpr int STAGE = evp_stage_bytes<K, CT, GSZ>();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float red[EVP_CW * Acc::NACC];
+  __shared__ int hist[Acc::NCELL];
+  __shared__ int cred[NG];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  StageRing ring;
+  ring.init(reinterpret_cast<uint64_t*>(smem_raw), ns, EVP_CW);
+  unsigned char* stage0 = smem_raw + 128;
+  for (int i = tid; i < Acc::NCELL; i += EVP_THREADS) hist[i] = 0;
+  if (tid < NG) cred[tid] = 0;
+  Groups<K, GSZ> gr;
+  gr.load(CT >= 1 ? table : nullptr);  // the level table is uploaded once per device: not produced by the previous kernel
+  const long g0 = (units_total * blockIdx.x / gridDim.x) * 16, g1 = (units_total * (blockIdx.x + 1) / gridDim.x) * 16;
+  int b = (int)(g0 / N);
+  long off = g0 - (long)b * N;
+  __syncthreads();
+  pdl_wait();
+
+  if (warp == EVP_CW) {
+    // ------------------------------ producer ------------------------------
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 1;
+      for (long cur = g0; cur < g1;) {
+        const int len = (int)min((long)EVP_PX, min(N - off, g1 - cur));
+        mbar_wait(ring.empty(slot), phase);
+        const uint32_t dst = smem_u32(stage0 + (size_t)slot * STAGE), bar = ring.full(slot);
+        const uint32_t bytes = (uint32_t)len * 4u;
+        uint32_t total = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          bulk_g2s_plain(dst + k * EVP_PX * 4, logits + ((size_t)b * K + k) * N + off, bytes, bar);
+          bulk_g2s_plain(dst + (K + k) * EVP_PX * 4, targets + (size_t)b * t_bstride + (size_t)k * t_cstride + off, bytes, bar);
+          total += 2 * bytes;
+        }
+        if constexpr (CONS) {
+#pragma unroll
+          for (int g = 0; g < NG; ++g)
+            if (g < gr.n) {
+              bulk_g2s_plain(dst + (2 * K + g) * EVP_PX * 4,
+                             parent_targets + (size_t)b * pt_bstride + (size_t)gr.parent[g] * pt_cstride + off, bytes, bar);
+              total += bytes;
+            }
+          bulk_g2s_plain(dst + (2 * K + NG) * EVP_PX * 4, prev_idx + (size_t)b * N + off, (uint32_t)len, bar);
+          total += (uint32_t)len;
+        }
+        mbar_arrive_expect_tx(bar, total);
+        if (++slot == ns) { slot = 0; phase ^= 1u; }
+        cur += len;
+        off += len;
+        if (off == N) { off = 0; ++b; }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------- consumers --------------------------------
+  auto csync = [] { consumer_sync(EVP_CONSUMERS); };
+  Acc ev;
+  ev.init();
+  int cur_b = b, slot = 0;
+  uint32_t phase = 0;
+  for (long cur = g0; cur < g1;) {
+    const int len = (int)min((long)EVP_PX, min(N - off, g1 - cur));
+    if (b != cur_b) {  // the range crosses into the next sample: hand over the finished sample's sums
+      ev.template finish<EVP_CW>(red, cred, hist, stats + (size_t)cur_b * K * RHSEG_NSTAT, cons, conf, tid, EVP_CONSUMERS, csync);
+      cur_b = b;
+    }
+    mbar_wait(ring.full(slot), phase);
+    const float* sf = reinterpret_cast<const float*>(stage0 + (size_t)slot * STAGE);
+    // full stages (all but the last of a sample or of the CTA's range) run code without any range predicate
+    auto body = [&](auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const bool ok = FULL ? true : tid * 4 < len;
+      float z[K][4], t[K][4], ptg[NG][4];
+      unsigned pidx4 = 0u;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float4 zv = *reinterpret_cast<const float4*>(sf + k * EVP_PX + tid * 4);
+        const float4 tv = *reinterpret_cast<const float4*>(sf + (K + k) * EVP_PX + tid * 4);
+        z[k][0] = zv.x; z[k][1] = zv.y; z[k][2] = zv.z; z[k][3] = zv.w;
+        t[k][0] = tv.x; t[k][1] = tv.y; t[k][2] = tv.z; t[k][3] = tv.w;
+      }
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        if (CONS && g < gr.n) {
+          const float4 pv = *reinterpret_cast<const float4*>(sf + (2 * K + g) * EVP_PX + tid * 4);
+          ptg[g][0] = pv.x; ptg[g][1] = pv.y; ptg[g][2] = pv.z; ptg[g][3] = pv.w;
+        } else {
+          ptg[g][0] = ptg[g][1] = ptg[g][2] = ptg[g][3] = -1.0f;
+        }
+      }
+      if constexpr (CONS) pidx4 = *reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(sf + (2 * K + NG) * EVP_PX) + tid * 4);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ring.empty(slot));  // the stage is in registers: the producer may refill the slot
+      unsigned my_idx = 0u;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float zz[K], tt[K], pg[NG], p[K], mx, sum;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { zz[k] = ok ? z[k][v] : 0.f; tt[k] = t[k][v]; }  // stale shared memory may hold NaNs
+#pragma unroll
+        for (int g = 0; g < NG; ++g) pg[g] = ptg[g][v];
+        softmax_all<K>(zz, p, mx, sum);
+        const int idx = ev.pixel(zz, p, mx + log_fast(sum), tt, pg, (int)((pidx4 >> (8 * v)) & 0xffu), ok, gr);
+        my_idx |= (unsigned)idx << (8 * v);
+      }
+      if (ok && idx_out) *reinterpret_cast<unsigned*>(idx_out + (size_t)b * N + off + tid * 4) = my_idx;
+    };
+    if (len == EVP_PX) body(std::true_type{});
+    else body(std::false_type{});
+    if (++slot == ns) { slot = 0; phase ^= 1u; }
+    cur += len;
+    off += len;
+    if (off == N) { off = 0; ++b; }
+  }
+  if (g0 < g1) ev.template finish<EVP_CW>(red, cred, hist, stats + (size_t)cur_b * K * RHSEG_NSTAT, cons, conf, tid, EVP_CONSUMERS, csync);
+}
+
+template <int K, int CT, int GSZ>
+static int launch_eval_pipe(const float* logits, const float* targets, long t_bs, long t_cs, const float* parent_targets,
+                            long pt_bs, long pt_cs, const unsigned char* prev_idx, const int32_t* table, int B, long N,
+                            double* stats, double* cons, unsigned long long* conf, unsigned char* idx_out, cudaStream_t st) {
+  auto kern = level_eval_pipe_kernel<K, CT, GSZ>;
+  constexpr int STAGE = evp_stage_bytes<K, CT, GSZ>();
+  static int tune = -1;
+  if (tune < 0) { const char* e = getenv("RHSEG_TUNE_EVAL"); tune = e ? atoi(e) : 0; }
+  const int ns = tune == 1 ? 3 : (tune == 2 ? 4 : 2);
+  const size_t smem = 128 + (size_t)ns * STAGE;
+  RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EVP_THREADS, smem));
+  if (per_sm < 1) return RHSEG_ERR_UNSUPPORTED;
+  const long units = (long)B * N / 16;
+  // every CTA gets at least two full stages of work; one resident wave at most
+  const long grid = std::max<long>(1, std::min<long>((long)device_sm_count() * per_sm, units / (2 * EVP_PX / 16)));
+  launch_pdl(kern, dim3((unsigned)grid), dim3(EVP_THREADS), smem, st, logits, targets, t_bs, t_cs, parent_targets, pt_bs, pt_cs,
+             prev_idx, table, N, units, ns, stats, cons, conf, idx_out);
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+// ------------------------------------------------------------------------------------
 // Flat -> hierarchy stitching (predictEval.py:85-185, :381-388): the flat model predicts the
 // leaves only; every node of the tree becomes one output channel: a leaf copies its flat channel,
 // a parent is the union (any > 0) of its descendant leaves.  Table driven: one uint32 leaf mask
@@ -320,9 +490,10 @@ extern "C" int rhseg_metric_ratios(const int64_t* conf, int nc, float* out5, voi
 extern "C" int rhseg_level_eval(const float* logits, const float* targets, long t_bstride, long t_cstride,
                                 const float* parent_targets, long pt_bstride, long pt_cstride,
                                 const unsigned char* prev_idx, const int32_t* table, int B, int K, int n_pix,
-                                int child, void* out_words, unsigned char* idx_out, int flags, void* stream) {
+                                int child_arg, void* out_words, unsigned char* idx_out, int flags, void* stream) {
   if (!logits || !targets || !out_words || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  const int child = child_arg & 1, hint = RHSEG_GROUP_HINT_OF(child_arg);
   if (child && !table) return RHSEG_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int nc = child ? K + 1 : K;
@@ -333,35 +504,31 @@ extern "C" int rhseg_level_eval(const float* logits, const float* targets, long 
   unsigned long long* conf = reinterpret_cast<unsigned long long*>(cons + RHSEG_MAX_K);
   const long N = n_pix;
   constexpr int THREADS = 256;
-  static int tune = -1;
-  if (tune < 0) { const char* e = getenv("RHSEG_TUNE_EVAL"); tune = e ? atoi(e) : 0; }
-  const int per_sm = tune == 1 ? 3 : 2;
-  const int slots = std::max(1, device_sm_count() * per_sm / B);  // CTAs per sample for one resident wave
   bool v4 = (N % 4 == 0) && aligned16(logits) && aligned16(targets) && t_bstride % 4 == 0 && t_cstride % 4 == 0 &&
             (reinterpret_cast<uintptr_t>(prev_idx) % 4 == 0) && (reinterpret_cast<uintptr_t>(idx_out) % 4 == 0);
   if (parent_targets) v4 = v4 && aligned16(parent_targets) && pt_bstride % 4 == 0 && pt_cstride % 4 == 0;
+  const bool cons_in = child && prev_idx != nullptr && parent_targets != nullptr;
+  const bool pipe = v4 && N % 16 == 0 && aligned16(prev_idx) && (long)B * N >= 4 * EVP_PX && !getenv("RHSEG_NO_EVAL_PIPE");
+  if (pipe) {
+    // level kind and group structure fixed at compile time: no flag tests per pixel
+    RHSEG_DISPATCH_K(K, {
+      if (!child)
+        return launch_eval_pipe<KK, 0, KK>(logits, targets, t_bstride, t_cstride, nullptr, 0, 0, nullptr, nullptr, B, N, stats, cons, conf, idx_out, st);
+      if (hint == KK) {
+        if (cons_in) return launch_eval_pipe<KK, 2, KK>(logits, targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, table, B, N, stats, cons, conf, idx_out, st);
+        return launch_eval_pipe<KK, 1, KK>(logits, targets, t_bstride, t_cstride, nullptr, 0, 0, nullptr, table, B, N, stats, cons, conf, idx_out, st);
+      }
+      if (cons_in) return launch_eval_pipe<KK, 2, 0>(logits, targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, table, B, N, stats, cons, conf, idx_out, st);
+      return launch_eval_pipe<KK, 1, 0>(logits, targets, t_bstride, t_cstride, nullptr, 0, 0, nullptr, table, B, N, stats, cons, conf, idx_out, st);
+    });
+  }
+  // generic path: any alignment, any size (level kind decided at run time)
+  const int slots = std::max(1, device_sm_count() * 2 / B);  // CTAs per sample for one resident wave
   RHSEG_DISPATCH_K(K, {
     if (v4) {
       dim3 grid((unsigned)balanced_grid((N + THREADS * 4 - 1) / (THREADS * 4), slots), B);
-      if (tune == 1)
-        launch_pdl(level_eval_kernel<KK, 4, 3, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
-            pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
-      else if (getenv("RHSEG_NO_CT_EVAL"))
-        launch_pdl(level_eval_kernel<KK, 4, 2, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
-            pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
-      else {
-        // level kind known at launch: three instantiations without flag tests in the per-pixel code
-        const int ct = !child ? 0 : ((prev_idx != nullptr && parent_targets != nullptr) ? 2 : 1);
-        if (ct == 0)
-          launch_pdl(level_eval_kernel<KK, 4, 2, THREADS, 0>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
-              pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
-        else if (ct == 1)
-          launch_pdl(level_eval_kernel<KK, 4, 2, THREADS, 1>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
-              pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
-        else
-          launch_pdl(level_eval_kernel<KK, 4, 2, THREADS, 2>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
-              pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
-      }
+      launch_pdl(level_eval_kernel<KK, 4, 2, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
+          pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     } else {
       dim3 grid((unsigned)balanced_grid((N + THREADS - 1) / THREADS, slots), B);
       launch_pdl(level_eval_kernel<KK, 1, 2, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,

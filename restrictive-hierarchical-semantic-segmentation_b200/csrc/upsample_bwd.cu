@@ -10,7 +10,9 @@
 //        targets, coefficients) + activation backward (sigmoid / restrictive softmax with the
 //        gradient arriving at the probabilities), so the hi-res gradient tensor never exists.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
+#include "hires.cuh"
 
 namespace rhseg {
 
@@ -186,43 +188,68 @@ upsample_adjoint_tiled_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, i
 }
 
 // ------------------------------------------------------------------------------------
-// Halo-free separable adjoint for row-aligned inputs (the HRNet case): pass 1 handles ROWS full
-// hi-res rows per CTA (every hi-res pixel's gradient is formed exactly once), reduces them along x
-// into tmpx [B,K,H,Wf]; pass 2 reduces tmpx along y.  Used when W % 4 == 0 and the taps per low-res
-// index fit XR_MAXW; the tiled kernel above is the generic fallback.
+// Band adjoint (the HRNet case: upsampling, W % 4 == 0, pre-zeroed dz_lo).  A CTA owns a band of consecutive hi-res
+// rows of one sample; consumer thread t owns the VEC pixels x0 = t*VEC .. of every row of the band.
+//   * a producer warp (one lane) streams one stage per hi-res row -- K logit rows, K target rows (+ parent
+//     probabilities / per-pixel probability gradients when the level receives them) -- by bulk async copy;
+//   * per row a consumer forms the gradient of its pixels exactly once (closed-form loss gradient + activation
+//     backward) and applies the adjoint of the y interpolation IN REGISTERS: row y feeds the low-res rows i0(y),
+//     i0(y)+1 with the forward's own lerp weights, so two running accumulators per pixel suffice;
+//   * whenever i0 advances (every ~scale rows) the finished accumulator row goes through shared memory once: the
+//     adjoint of the x interpolation (tabulated taps per low-res column) and one fp32 add into the pre-zeroed dz_lo.
+//     Only the first / last low-res row of a band is shared with the neighbouring band, so every dz_lo element
+//     receives at most two terms: the fp32 result does not depend on the order (deterministic).
+// dz_hi, the former tmpx [B,K,H,Wf] and a second kernel never exist; the x reduction runs once per low-res row
+// instead of once per hi-res row.
+// SRC 0: dz_hi is read from memory (drop-in route, what autograd hands us);  SRC 1: formed on the fly.
+// ACTK (SRC 1): 1 = no gradient reaches the level's probabilities (last level), 2 = sigmoid level that only
+// receives the uniform FiLM-pool gradient (level 0 of a two-level tree), 0 = decided at run time (deeper trees).
 // ------------------------------------------------------------------------------------
-constexpr int XR_MAXROWS = 8, XR_THREADS = 256, XR_MAXW = 12;
+constexpr int XR_MAXW = 12;  // max hi-res taps per low-res column held in the weight table (upsampling factor <= ~5)
 
-// BAND: the CTA owns `band` consecutive hi-res rows; each x-reduced row is scattered straight into a
-// shared-memory accumulator of the few low-res rows the band touches (adjoint of the y interpolation: row y
-// feeds rows i0(y), i1(y) with the forward's own lerp weights) and the accumulator is added into a
-// PRE-ZEROED dz_lo at the end.  band >= taps per low-res row, so a low-res row receives from at most two
-// CTAs and the two-term fp32 sum is order independent: deterministic, no tmpx tensor, no second kernel.
-// ACTK: what the launcher knows about the gradient reaching this level's probabilities: 0 = decide at run time,
-// 1 = none (last level of the tree: the activation backward is compiled out), 2 = sigmoid level that only receives
-// the uniform FiLM-pool gradient (level 0 of a two-level tree: no per-pixel term, nothing to hand to a parent).
-// Kinds 1 and 2 fit 64 registers and run 512-thread CTAs (twice the warps per SM).
-template <int K, int SRC, int MODE, bool BAND = false, int ACTK = 0, int THREADS = XR_THREADS>
-__global__ void __launch_bounds__(THREADS, 2)
-dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, int H, int W, float sx, int XR_ROWS,
-                       float* __restrict__ tmpx, int Hf, float sy, int band, int acc_rows, float* __restrict__ dz_lo) {
-  pdl_wait();
-  extern __shared__ __align__(16) float sm[];
-  const int Wp = W + 4;
-  float* dzs = sm;                                   // [K][XR_ROWS][Wp]
-  float* wtab = sm + (size_t)K * XR_ROWS * Wp;       // [Wf][XR_MAXW]
-  int* wstart = reinterpret_cast<int*>(wtab + (size_t)Wf * XR_MAXW);  // [Wf]
-  int* wcnt = wstart + Wf;                           // [Wf]
-  float* accs = reinterpret_cast<float*>(wcnt + Wf); // BAND: [K][acc_rows][Wf]
-  const int b = blockIdx.y, tid = threadIdx.x;
+template <int K, int GSZ>
+__device__ __forceinline__ void group_sum_g(const float (&x)[K], const Groups<K, GSZ>& gr, float (&out)[K]) {
+  if constexpr (GSZ == 0) {
+    group_sum<K>(x, gr.start_mask, out);
+  } else {
+#pragma unroll
+    for (int g = 0; g < K / GSZ; ++g) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < GSZ; ++j) s += x[g * GSZ + j];
+#pragma unroll
+      for (int j = 0; j < GSZ; ++j) out[g * GSZ + j] = s;
+    }
+  }
+}
+
+template <int K, int VEC, int SRC, int MODE, int ACTK, int GSZ>
+__global__ void __launch_bounds__(VEC == 4 ? 192 + 32 : 384 + 32)
+dz_band_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, int H, int W, float sy, float sx, int band,
+               int ns, int n_dp, float* __restrict__ dz_lo) {
+  constexpr bool GROUPED = MODE == RHSEG_ACT_GROUPED;
+  constexpr bool NOACT = SRC == 0 || ACTK == 1 || MODE == RHSEG_ACT_ZEROS, UNIF = SRC == 1 && ACTK == 2;
+  static_assert(!UNIF || MODE == RHSEG_ACT_SIGMOID, "uniform-only kind: sigmoid levels");
+  constexpr int NG = Groups<K, GSZ>::NG;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncons = (int)blockDim.x - 32, ncw = ncons >> 5;
+  const int b = blockIdx.y;
+  const int y_begin = blockIdx.x * band, y_end = min(H, y_begin + band);
   const long N = (long)H * W;
-  const int band_y0 = BAND ? blockIdx.x * band : 0;
-  const int band_y1 = BAND ? min(H, band_y0 + band) : H;
-  const int i_lo = BAND ? make_lerp(band_y0, sy, Hf).i0 : 0;
-  if constexpr (BAND)
-    for (int e = tid; e < K * acc_rows * Wf; e += THREADS) accs[e] = 0.f;
+  const int TP = W + XR_MAXW;  // pitch of a flush row (taps past the row end carry weight 0)
 
-  for (int j = tid; j < Wf; j += THREADS) {
+  StageRing ring;
+  ring.init(reinterpret_cast<uint64_t*>(smem_raw), ns, ncw);
+  float* wtab = reinterpret_cast<float*>(smem_raw + 128);              // [Wf][XR_MAXW]
+  int* wstart = reinterpret_cast<int*>(wtab + (size_t)Wf * XR_MAXW);   // [Wf]
+  int* wcnt = wstart + Wf;                                             // [Wf]
+  float* Tbuf = reinterpret_cast<float*>(smem_raw + ((128 + (size_t)Wf * (XR_MAXW + 2) * 4 + 15) & ~(size_t)15));  // [2][K][TP]
+  size_t t_end = (size_t)(reinterpret_cast<unsigned char*>(Tbuf + 2 * (size_t)K * TP) - smem_raw);
+  unsigned char* stage0 = smem_raw + ((t_end + 127) & ~(size_t)127);
+
+  // taps of the x adjoint: low-res column j receives from the contiguous run of hi-res columns that read it
+  for (int j = tid; j < Wf; j += blockDim.x) {
     int lo, hi;
     lerp_support(j, sx, W, lo, hi);
     int first = -1, cnt = 0;
@@ -234,161 +261,294 @@ dz_rows_xreduce_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Wf, 
         ++cnt;
       }
     }
+    for (int q = cnt; q < XR_MAXW; ++q) wtab[j * XR_MAXW + q] = 0.f;
     wstart[j] = first < 0 ? lo : first;
     wcnt[j] = cnt < XR_MAXW ? cnt : XR_MAXW;
   }
+  for (int e = tid; e < 2 * K * TP; e += blockDim.x) Tbuf[e] = 0.f;  // the pad columns stay zero
 
-  // persistent over the sample's row blocks (the weight tables above are built once per CTA)
-  const int vec_per_row = W / 4;
-  for (int y0 = BAND ? band_y0 : blockIdx.x * XR_ROWS; y0 < band_y1; y0 += BAND ? XR_ROWS : gridDim.x * XR_ROWS) {
-  const int rows = min(XR_ROWS, band_y1 - y0);
-  __syncthreads();  // tables ready / previous block's readers done
-  // ---- phase 1: gradient of ROWS full rows -> shared memory (4 pixels per thread and step) ----
-  if constexpr (SRC == 0) {
-    for (int e = tid; e < rows * vec_per_row; e += THREADS) {
-      const int r = e / vec_per_row, xv = (e - r * vec_per_row) * 4;
-      const size_t px = (size_t)(y0 + r) * W + xv;
+  Groups<K, GSZ> gr;
+  gr.load((SRC == 1 && GROUPED) ? fa.table : nullptr);
+  const bool has_act = UNIF || (!NOACT && (fa.g_uniform != nullptr || (fa.dp_pix != nullptr && fa.pix_mask != 0)));
+  const int n_pp = (GROUPED && !NOACT && has_act) ? gr.n : 0;
+  const int n_dpr = (!NOACT && !UNIF && has_act && fa.dp_pix != nullptr) ? n_dp : 0;  // rows of dp_pix (channels in pix_mask)
+  const uint32_t rowb = (uint32_t)W * 4u;
+  // stage layout: SRC 0: [K dz rows];  SRC 1: [K logit rows][K target rows][n_pp parent-probability rows][n_dpr dP rows]
+  const uint32_t stage_bytes = (uint32_t)(SRC == 0 ? K : 2 * K + n_pp + n_dpr) * rowb;
+  __syncthreads();
+
+  if (warp == ncw) {
+    // ------------------------------ producer ------------------------------
+    if (lane == 0) {
+      pdl_wait();
+      int slot = 0;
+      uint32_t phase = 1;
+      for (int y = y_begin; y < y_end; ++y) {
+        mbar_wait(ring.empty(slot), phase);
+        uint32_t dst = smem_u32(stage0 + (size_t)slot * stage_bytes);
+        const uint32_t bar = ring.full(slot);
+        const long px = (long)y * W;
+        if constexpr (SRC == 0) {
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const float4 v = *reinterpret_cast<const float4*>(dz_hi + ((size_t)b * K + k) * N + px);
-        *reinterpret_cast<float4*>(dzs + ((size_t)k * XR_ROWS + r) * Wp + xv) = v;
+          for (int k = 0; k < K; ++k) { bulk_g2s_plain(dst, dz_hi + ((size_t)b * K + k) * N + px, rowb, bar); dst += rowb; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; ++k) { bulk_g2s_plain(dst, fa.logits + ((size_t)b * K + k) * N + px, rowb, bar); dst += rowb; }
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            bulk_g2s_plain(dst, fa.targets + (size_t)b * fa.t_bstride + (size_t)k * fa.t_cstride + px, rowb, bar);
+            dst += rowb;
+          }
+          if constexpr (GROUPED && !NOACT) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+              if (g < n_pp) { bulk_g2s_plain(dst, fa.prev_probs + ((size_t)b * fa.K_prev + gr.parent[g]) * N + px, rowb, bar); dst += rowb; }
+          }
+          if constexpr (!NOACT && !UNIF) {
+            if (n_dpr) {
+#pragma unroll
+              for (int k = 0; k < K; ++k)
+                if ((fa.pix_mask >> k) & 1u) { bulk_g2s_plain(dst, fa.dp_pix + ((size_t)b * K + k) * N + px, rowb, bar); dst += rowb; }
+            }
+          }
+        }
+        mbar_arrive_expect_tx(bar, stage_bytes);
+        if (++slot == ns) { slot = 0; phase ^= 1u; }
       }
     }
-  } else {
-    const LevelInfo li = load_level_info<K>(MODE == RHSEG_ACT_GROUPED ? fa.table : nullptr);
+    return;
+  }
+
+  // -------------------------------- consumers --------------------------------
+  auto csync = [ncons] { consumer_sync(ncons); };
+  const int x0 = tid * VEC;
+  const bool ok = x0 < W;  // W % VEC == 0 (launcher)
+  const int xr = ok ? x0 : 0;
+  float A[K], Bc[K], Cc[K], gu[K];
+  pdl_wait();  // coef / g_uniform are produced by the previous kernels; dz_lo was zeroed by one
+  if constexpr (SRC == 1) {
     const float gce = fa.g_ce ? __ldg(fa.g_ce) : 0.f, gdi = fa.g_dice ? __ldg(fa.g_dice) : 0.f;
-    float A[K], Bc[K], Cc[K], gu[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const float* cf = fa.coef + ((size_t)b * K + k) * 3;
       A[k] = gce * __ldg(cf);
       Bc[k] = gdi * __ldg(cf + 1);
       Cc[k] = gdi * __ldg(cf + 2);
-      gu[k] = fa.g_uniform ? (float)fa.g_uniform[b * K + k] * fa.inv_npix : 0.f;
+      gu[k] = (!NOACT && fa.g_uniform) ? (float)fa.g_uniform[b * K + k] * fa.inv_npix : 0.f;
     }
-    constexpr bool NOACT = ACTK == 1, UNIF = ACTK == 2;
-    static_assert(!UNIF || MODE == RHSEG_ACT_SIGMOID, "uniform-only kind: sigmoid levels");
-    const bool has_act = UNIF || (!NOACT && MODE != RHSEG_ACT_ZEROS && (fa.g_uniform != nullptr || (fa.dp_pix != nullptr && fa.pix_mask != 0)));
-    for (int e = tid; e < rows * vec_per_row; e += THREADS) {
-      const int r = e / vec_per_row, xv = (e - r * vec_per_row) * 4;
-      const size_t px = (size_t)(y0 + r) * W + xv;
-      float z[K][4], t[K][4], ex[K][4], pp[K][4], o[K][4], dpar[K][4];
+  }
+  float accA[K][VEC], accB[K][VEC];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { accA[k][v] = 0.f; accB[k][v] = 0.f; }
+  int cur = make_lerp(y_begin, sy, Hf).i0;  // low-res row accA belongs to (accB: cur + 1)
+  int tb = 0;
+
+  // finished low-res row -> shared memory -> adjoint of the x interpolation -> += dz_lo
+  auto flush = [&](const float (&acc)[K][VEC], int i_row) {
+    float* T = Tbuf + (size_t)tb * K * TP;
+    if (ok) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const Vec<4> zv = ld_stream<4>(fa.logits + ((size_t)b * K + k) * N + px);
-        const Vec<4> tv = ld_cached<4>(fa.targets + (size_t)b * fa.t_bstride + (size_t)k * fa.t_cstride + px);
-        Vec<4> ev;
+        Vec<VEC> o;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) ev.v[v] = 0.f;
-        if (!UNIF && has_act && fa.dp_pix && ((fa.pix_mask >> k) & 1u)) ev = ld_stream<4>(fa.dp_pix + ((size_t)b * K + k) * N + px);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) { z[k][v] = zv.v[v]; t[k][v] = tv.v[v]; ex[k][v] = ev.v[v]; pp[k][v] = 0.f; }
+        for (int v = 0; v < VEC; ++v) o.v[v] = acc[k][v];
+        *reinterpret_cast<Vec<VEC>*>(T + (size_t)k * TP + x0) = o;
       }
-      if constexpr (MODE == RHSEG_ACT_GROUPED) {
-        if (has_act) {
+    }
+    csync();
+    for (int j = tid; j < Wf; j += ncons) {
+      const float* wt = wtab + j * XR_MAXW;
+      const int ws = wstart[j], n = wcnt[j];
 #pragma unroll
-          for (int k = 0; k < K; ++k) {
-            if ((li.start_mask >> k) & 1) {
-              const Vec<4> pv = ld_stream<4>(fa.prev_probs + ((size_t)b * fa.K_prev + li.parent[k]) * N + px);
+      for (int k = 0; k < K; ++k) {
+        const float* row = T + (size_t)k * TP + ws;
+        float a = 0.f;
+        for (int q = 0; q < n; ++q) a = fmaf(wt[q], row[q], a);
+        atomicAdd(dz_lo + (((size_t)b * K + k) * Hf + i_row) * Wf + j, a);
+      }
+    }
+    tb ^= 1;  // the next flush writes the other buffer: its barrier orders it after this one's readers
+  };
+
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int y = y_begin; y < y_end; ++y) {
+    const Lerp ly = make_lerp(y, sy, Hf);
+    mbar_wait(ring.full(slot), phase);
+    const float* sf = reinterpret_cast<const float*>(stage0 + (size_t)slot * stage_bytes) + xr;
+    float dz[K][VEC];
+    if constexpr (SRC == 0) {
 #pragma unroll
-              for (int v = 0; v < 4; ++v) pp[k][v] = pv.v[v];
-            } else {
+      for (int k = 0; k < K; ++k) {
+        const Vec<VEC> dv = *reinterpret_cast<const Vec<VEC>*>(sf + (size_t)k * W);
 #pragma unroll
-              for (int v = 0; v < 4; ++v) pp[k][v] = pp[k > 0 ? k - 1 : 0][v];
-            }
+        for (int v = 0; v < VEC; ++v) dz[k][v] = ok ? dv.v[v] : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ring.empty(slot));
+    } else {
+      float z[K][VEC], t[K][VEC], ppg[NG][VEC], ex[K][VEC];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const Vec<VEC> zv = *reinterpret_cast<const Vec<VEC>*>(sf + (size_t)k * W);
+        const Vec<VEC> tv = *reinterpret_cast<const Vec<VEC>*>(sf + (size_t)(K + k) * W);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { z[k][v] = ok ? zv.v[v] : 0.f; t[k][v] = ok ? tv.v[v] : -1.f; ex[k][v] = 0.f; }
+      }
+      int row = 2 * K;
+      if constexpr (GROUPED && !NOACT) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) ppg[g][v] = 0.f;
+          if (g < n_pp) {
+            const Vec<VEC> pv = *reinterpret_cast<const Vec<VEC>*>(sf + (size_t)(row++) * W);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) ppg[g][v] = ok ? pv.v[v] : 0.f;
           }
         }
       }
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        float zz[K], tt[K], dz[K], dP[K], ppv[K], dpv[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) { zz[k] = z[k][v]; tt[k] = t[k][v]; dP[k] = gu[k] + ex[k][v]; ppv[k] = pp[k][v]; dpv[k] = 0.f; }
-        loss_dz_pixel<K, true>(zz, tt, A, Bc, Cc, dz);
-        if (has_act) act_dz_pixel<K, MODE>(zz, dP, ppv, li.start_mask, dz, dpv);
-#pragma unroll
-        for (int k = 0; k < K; ++k) { o[k][v] = dz[k]; dpar[k][v] = dpv[k]; }
-      }
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-        *reinterpret_cast<float4*>(dzs + ((size_t)k * XR_ROWS + r) * Wp + xv) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
-      if constexpr (MODE == RHSEG_ACT_GROUPED) {
-        if (has_act && fa.dp_prev) {
+      if constexpr (!NOACT && !UNIF) {
+        if (n_dpr) {
 #pragma unroll
           for (int k = 0; k < K; ++k)
-            if ((li.start_mask >> k) & 1) {
-              float* dst = fa.dp_prev + ((size_t)b * fa.K_prev + li.parent[k]) * N + px;
-              float4 cur = *reinterpret_cast<const float4*>(dst);
-              cur.x += dpar[k][0]; cur.y += dpar[k][1]; cur.z += dpar[k][2]; cur.w += dpar[k][3];
-              *reinterpret_cast<float4*>(dst) = cur;
+            if ((fa.pix_mask >> k) & 1u) {
+              const Vec<VEC> ev = *reinterpret_cast<const Vec<VEC>*>(sf + (size_t)(row++) * W);
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) ex[k][v] = ok ? ev.v[v] : 0.f;
+            }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ring.empty(slot));  // the row is in registers
+      float dpar[NG][VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float zz[K], tt[K], o[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { zz[k] = z[k][v]; tt[k] = t[k][v]; }
+        loss_dz_pixel<K, true>(zz, tt, A, Bc, Cc, o);
+        if constexpr (UNIF) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const float p = sigmoidf_ref(zz[k]);
+            o[k] = fmaf(gu[k], p * (1.0f - p), o[k]);
+          }
+        } else if constexpr (!NOACT) {
+          if (has_act) {
+            if constexpr (MODE == RHSEG_ACT_SIGMOID) {
+#pragma unroll
+              for (int k = 0; k < K; ++k) {
+                const float p = sigmoidf_ref(zz[k]);
+                o[k] = fmaf(gu[k] + ex[k][v], p * (1.0f - p), o[k]);
+              }
+            } else {
+              // P_c = P_p Q_c: dQ_c = dP_c P_p; dz += Q (dQ - sum_group dQ Q); dP_p = sum_group dP_c Q_c
+              float q[K], dpq[K], dq_q[K], inner[K], dpp[K], pg[NG];
+#pragma unroll
+              for (int g = 0; g < NG; ++g) pg[g] = ppg[g][v];
+              softmax_groups<K, GSZ>(zz, gr, q);
+#pragma unroll
+              for (int k = 0; k < K; ++k) {
+                dpq[k] = (gu[k] + ex[k][v]) * q[k];
+                dq_q[k] = dpq[k] * group_value<K, GSZ>(pg, gr, k);
+              }
+              group_sum_g<K, GSZ>(dq_q, gr, inner);
+              group_sum_g<K, GSZ>(dpq, gr, dpp);
+#pragma unroll
+              for (int k = 0; k < K; ++k) o[k] += dq_q[k] - q[k] * inner[k];
+              // the group's sum sits at every member: pick the value at the group's first channel
+#pragma unroll
+              for (int g = 0; g < NG; ++g) {
+                float val = 0.f;
+                if constexpr (GSZ > 0) val = dpp[g * GSZ];
+                else {
+                  int seen = 0;
+#pragma unroll
+                  for (int k = 0; k < K; ++k)
+                    if ((gr.start_mask >> k) & 1) { if (seen == g) val = dpp[k]; ++seen; }
+                }
+                dpar[g][v] = val;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) dz[k][v] = o[k];
+      }
+      if constexpr (GROUPED && !NOACT) {
+        if (has_act && fa.dp_prev && ok) {  // every hi-res pixel is visited exactly once: plain stores
+#pragma unroll
+          for (int g = 0; g < NG; ++g)
+            if (g < n_pp) {
+              Vec<VEC> o;
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) o.v[v] = dpar[g][v];
+              *reinterpret_cast<Vec<VEC>*>(fa.dp_prev + ((size_t)b * fa.K_prev + gr.parent[g]) * N + (size_t)y * W + x0) = o;
             }
         }
       }
     }
-  }
-  __syncthreads();
-
-  // ---- phase 2: reduce along x: tmpx[b][k][y][j] = sum_x wx(x, j) dz[k][y][x] ----
-  if constexpr (BAND) {
-    // thread <-> (k, j) column: it alone touches accs[k][*][j]
-    for (int e = tid; e < K * Wf; e += THREADS) {
-      const int k = e / Wf, j = e - k * Wf;
-      const float* wt = wtab + j * XR_MAXW;
-      const int n = wcnt[j], ws = wstart[j];
-      for (int r = 0; r < rows; ++r) {
-        const float* row = dzs + ((size_t)k * XR_ROWS + r) * Wp + ws;
-        float acc = 0.f;
-        for (int q = 0; q < n; ++q) acc = fmaf(wt[q], row[q], acc);
-        const Lerp ly = make_lerp(y0 + r, sy, Hf);
-        float* col = accs + ((long)k * acc_rows - i_lo) * Wf + j;
-        col[(long)ly.i0 * Wf] = fmaf(ly.l0, acc, col[(long)ly.i0 * Wf]);
-        col[(long)ly.i1 * Wf] = fmaf(ly.l1, acc, col[(long)ly.i1 * Wf]);
+    if (++slot == ns) { slot = 0; phase ^= 1u; }
+    // adjoint of the y interpolation in registers
+    while (cur < ly.i0) {  // uniform over the CTA
+      flush(accA, cur);
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { accA[k][v] = accB[k][v]; accB[k][v] = 0.f; }
+      ++cur;
+    }
+    const bool two = ly.i1 > ly.i0;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        accA[k][v] = fmaf(ly.l0, dz[k][v], accA[k][v]);
+        if (two) accB[k][v] = fmaf(ly.l1, dz[k][v], accB[k][v]);
+        else accA[k][v] = fmaf(ly.l1, dz[k][v], accA[k][v]);
       }
-    }
-  } else
-  for (int e = tid; e < K * rows * Wf; e += THREADS) {
-    const int j = e % Wf;
-    const int kr = e / Wf;
-    const int r = kr % rows, k = kr / rows;
-    const float* row = dzs + ((size_t)k * XR_ROWS + r) * Wp + wstart[j];
-    const float* wt = wtab + j * XR_MAXW;
-    const int n = wcnt[j];
-    float acc = 0.f;
-    for (int q = 0; q < n; ++q) acc = fmaf(wt[q], row[q], acc);
-    tmpx[(((size_t)b * K + k) * H + y0 + r) * Wf + j] = acc;
   }
-  }  // row blocks
-  if constexpr (BAND) {
-    __syncthreads();
-    const int i_hi = make_lerp(band_y1 - 1, sy, Hf).i1;
-    const int nrow = i_hi - i_lo + 1;
-    for (int e = tid; e < K * nrow * Wf; e += THREADS) {
-      const int j = e % Wf;
-      const int kr = e / Wf;
-      const int ri = kr % nrow, k = kr / nrow;
-      atomicAdd(dz_lo + (((size_t)b * K + k) * Hf + i_lo + ri) * Wf + j, accs[((size_t)k * acc_rows + ri) * Wf + j]);
-    }
+  if (y_begin < y_end) {
+    flush(accA, cur);
+    if (cur + 1 < Hf) flush(accB, cur + 1);
   }
 }
 
-// pass 2: dz_lo[b][k][i][j] = sum_y wy(y, i) tmpx[b][k][y][j]
-__global__ void __launch_bounds__(256)
-yreduce_kernel(const float* __restrict__ tmpx, int Hf, int Wf, int H, float sy, long total, float* __restrict__ dz_lo) {
-  pdl_wait();
-  const long idx = (long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const int j = (int)(idx % Wf);
-  const int i = (int)((idx / Wf) % Hf);
-  const long bk = idx / ((long)Wf * Hf);
-  int lo, hi;
-  lerp_support(i, sy, H, lo, hi);
-  const float* col = tmpx + (size_t)bk * H * Wf + j;
-  float acc = 0.f;
-  for (int y = lo; y <= hi; ++y) {
-    const float w = lerp_weight(y, sy, Hf, i);
-    if (w != 0.f) acc = fmaf(w, __ldg(col + (size_t)y * Wf), acc);
-  }
-  dz_lo[idx] = acc;
+template <int K, int VEC, int SRC, int MODE, int ACTK, int GSZ>
+static int launch_dz_band(const float* dz_hi, const FusedDzArgs& fa, int B, int Hf, int Wf, int H, int W, float sy, float sx,
+                          float* dz_lo, cudaStream_t st, bool* launched) {
+  *launched = false;
+  auto kern = dz_band_kernel<K, VEC, SRC, MODE, ACTK, GSZ>;
+  const int ncons = ((W / VEC + 31) / 32) * 32;
+  if (ncons > (VEC == 4 ? 192 : 384)) return RHSEG_OK;
+  int n_dp = 0;
+  for (int k = 0; k < K; ++k) n_dp += (fa.pix_mask >> k) & 1u;
+  // worst-case stage (the kernel derives the actual row count from the table / flags)
+  const int rows = SRC == 0 ? K : 2 * K + ((MODE == RHSEG_ACT_GROUPED && ACTK == 0) ? Groups<K, GSZ>::NG : 0) + (ACTK == 0 ? n_dp : 0);
+  const size_t stage = (size_t)rows * W * 4;
+  static int tune_ns = -1;
+  if (tune_ns < 0) { const char* e = getenv("RHSEG_TUNE_DZ_NS"); tune_ns = e ? atoi(e) : 0; }
+  const int ns = tune_ns > 0 ? std::min(tune_ns, 7) : 3;
+  size_t fixed = ((128 + (size_t)Wf * (XR_MAXW + 2) * 4 + 15) & ~(size_t)15) + 2 * (size_t)K * (W + XR_MAXW) * 4;
+  fixed = (fixed + 127) & ~(size_t)127;
+  const size_t smem = fixed + (size_t)ns * stage;
+  if (smem > 200 * 1024) return RHSEG_OK;
+  RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ncons + 32, smem));
+  if (per_sm < 1) return RHSEG_OK;
+  const long slots = std::max<long>(1, (long)per_sm * device_sm_count() / B);
+  // >= taps per low-res row, so that at most two CTAs feed one low-res row
+  const int min_band = std::max(4, (int)ceilf(2.0f / sy));
+  const int band = std::max(min_band, (int)((H + slots - 1) / slots));
+  dim3 grid((unsigned)((H + band - 1) / band), B);
+  launch_pdl(kern, dim3(grid), dim3(ncons + 32), smem, st, dz_hi, fa, Hf, Wf, H, W, sy, sx, band, ns, n_dp, dz_lo);
+  RHSEG_LAUNCH_CHECK();
+  *launched = true;
+  return RHSEG_OK;
 }
 
 // Full-resolution donors (UNet): the same fused per-pixel gradient, written out once as dz.
@@ -478,86 +638,45 @@ static int region_extent(int t, float scale, int out_size) {
 }
 
 template <int K, int SRC, int MODE>
-static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int B, int Hf, int Wf, int H, int W, float* dz_lo,
-                          float* tmpx, bool prezeroed, cudaStream_t st) {
+static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int hint, int B, int Hf, int Wf, int H, int W, float* dz_lo,
+                          bool prezeroed, cudaStream_t st) {
   const float sy = H > 1 ? (float)(Hf - 1) / (float)(H - 1) : 0.f;
   const float sx = W > 1 ? (float)(Wf - 1) / (float)(W - 1) : 0.f;
-  {
+  if constexpr (MODE != RHSEG_ACT_ZEROS || SRC == 0) {
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    bool rows_ok = (tmpx != nullptr || prezeroed) && W % 4 == 0 && sx > 0.f && 2.0f / sx + 3.0f <= (float)XR_MAXW;
-    if (SRC == 0) rows_ok = rows_ok && al(dz_hi);
-    else rows_ok = rows_ok && al(fa.logits) && al(fa.targets) && fa.t_bstride % 4 == 0 && fa.t_cstride % 4 == 0 &&
+    bool band_ok = prezeroed && W % 4 == 0 && sx > 0.f && sy > 0.f && sy <= 1.0f && 2.0f / sx + 3.0f <= (float)XR_MAXW &&
+                   !getenv("RHSEG_NO_BAND_ADJOINT");
+    if (SRC == 0) band_ok = band_ok && al(dz_hi);
+    else band_ok = band_ok && al(fa.logits) && al(fa.targets) && fa.t_bstride % 4 == 0 && fa.t_cstride % 4 == 0 &&
                    al(fa.prev_probs) && al(fa.dp_pix) && al(fa.dp_prev);
-    constexpr int ROWS = 2;  // rows per block: small blocks, the persistent loop balances them over one wave
-    const size_t smem = ((size_t)K * ROWS * (W + 4) + (size_t)Wf * XR_MAXW + 2 * (size_t)Wf) * sizeof(float);
-    const bool no_band = getenv("RHSEG_NO_BAND_ADJOINT") != nullptr;
-    if (rows_ok && prezeroed && !no_band && sy > 0.f && sy <= 1.0f) {
-      // band kernel: x- and y-reduction in one pass into the pre-zeroed dz_lo
-      // without the activation backward the kernel needs 64 registers: 512-thread CTAs double the warps per SM
+    if (band_ok) {
+      static int tune_vec = -1;
+      if (tune_vec < 0) { const char* e = getenv("RHSEG_TUNE_DZ_VEC"); tune_vec = e ? atoi(e) : 0; }
       const bool no_pix = fa.dp_pix == nullptr || fa.pix_mask == 0;
-      const bool no_act = SRC == 1 && (MODE == RHSEG_ACT_ZEROS || (fa.g_uniform == nullptr && no_pix));
+      const bool no_act = SRC == 1 && fa.g_uniform == nullptr && no_pix;
       const bool unif = SRC == 1 && MODE == RHSEG_ACT_SIGMOID && fa.g_uniform != nullptr && no_pix;
-      const int nthreads = (no_act || unif) ? 2 * XR_THREADS : XR_THREADS;
-      constexpr int T2 = (SRC == 1) ? 2 * XR_THREADS : XR_THREADS;
-      auto kern = no_act ? dz_rows_xreduce_kernel<K, SRC, MODE, true, (SRC == 1 ? 1 : 0), T2>
-                : unif   ? dz_rows_xreduce_kernel<K, SRC, MODE, true, ((SRC == 1 && MODE == RHSEG_ACT_SIGMOID) ? 2 : 0),
-                                                  ((SRC == 1 && MODE == RHSEG_ACT_SIGMOID) ? T2 : XR_THREADS)>
-                         : dz_rows_xreduce_kernel<K, SRC, MODE, true, 0, XR_THREADS>;
-      // >= taps per low-res row (ceil(2/sy) - 1 would do): at most two CTAs feed one low-res row
-      const int min_band = std::max(2, (int)ceilf(2.0f / sy));
-      // rows per phase-1 pass: the one that wastes the fewest threads (a pass handles rows * W/4 four-pixel items
-      // with nthreads threads: 2 rows of 620 px keep only 60 % of them busy, 3 rows 91 %)
-      const int vpr = W / 4;
-      int sub = 1;
-      double best_util = 0.0;
-      for (int r = 1; r <= 4; ++r) {
-        const int items = r * vpr;
-        const double util = (double)items / (double)(((items + nthreads - 1) / nthreads) * nthreads);
-        if (util > best_util + 1e-9) { best_util = util; sub = r; }
+      bool done = false;
+      int rc = RHSEG_OK;
+#define RHSEG_DZB(VEC, ACTK, GS) rc = launch_dz_band<K, VEC, SRC, MODE, ACTK, GS>(dz_hi, fa, B, Hf, Wf, H, W, sy, sx, dz_lo, st, &done)
+#define RHSEG_DZB_V(ACTK, GS)                                   \
+      do {                                                      \
+        if (tune_vec != 2) RHSEG_DZB(4, ACTK, GS);              \
+        if (!done && rc == RHSEG_OK) RHSEG_DZB(2, ACTK, GS);    \
+      } while (0)
+      if constexpr (SRC == 0) {
+        RHSEG_DZB_V(1, K);
+      } else if constexpr (MODE == RHSEG_ACT_SIGMOID) {
+        if (no_act) RHSEG_DZB_V(1, K); else if (unif) RHSEG_DZB_V(2, K); else RHSEG_DZB_V(0, K);
+      } else {
+        if (no_act) RHSEG_DZB_V(1, K); else if (hint == K) RHSEG_DZB_V(0, K); else RHSEG_DZB_V(0, 0);
       }
-      auto smem_for = [&](int band) {
-        const int acc_rows = (int)floorf(sy * (float)band) + 4;
-        return ((size_t)K * sub * (W + 4) + (size_t)Wf * XR_MAXW + 2 * (size_t)Wf + (size_t)K * acc_rows * Wf) * sizeof(float);
-      };
-      auto round_band = [&](int band) { return ((std::max(band, min_band) + sub - 1) / sub) * sub; };
-      int per_sm = 0;
-      const size_t smem0 = smem_for(round_band(min_band));
-      if (smem0 <= 200 * 1024) {
-        if (smem0 > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-        RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem0));
-      }
-      if (per_sm >= 1) {
-        const long slots = std::max<long>(1, (long)per_sm * device_sm_count() / B);
-        const int band = round_band((int)((H + slots - 1) / slots));
-        const int acc_rows = (int)floorf(sy * (float)band) + 4;
-        const size_t smem_b = smem_for(band);
-        if (smem_b <= 200 * 1024) {
-          if (smem_b > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-          dim3 grid((unsigned)((H + band - 1) / band), B);
-          launch_pdl(kern, dim3(grid), dim3(nthreads), smem_b, st, dz_hi, fa, Wf, H, W, sx, sub, (float*)nullptr, Hf, sy, band,
-                     acc_rows, dz_lo);
-          RHSEG_LAUNCH_CHECK();
-          return RHSEG_OK;
-        }
-      }
-    }
-    if (prezeroed && tmpx == nullptr) rows_ok = false;  // two-kernel row path needs the workspace
-    auto kern = dz_rows_xreduce_kernel<K, SRC, MODE>;
-    if (rows_ok && smem <= 200 * 1024) {
-      if (smem > 48 * 1024) RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int per_sm = 0;
-      RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, XR_THREADS, smem));
-      if (per_sm < 1) per_sm = 1;
-      const long slots = std::max<long>(1, (long)per_sm * device_sm_count() / B);
-      dim3 grid(balanced_grid((H + ROWS - 1) / ROWS, slots), B);
-      launch_pdl(kern, dim3(grid), dim3(XR_THREADS), smem, st, dz_hi, fa, Wf, H, W, sx, ROWS, tmpx, Hf, sy, 0, 0, (float*)nullptr);
-      RHSEG_LAUNCH_CHECK();
-      const long total = (long)B * K * Hf * Wf;
-      launch_pdl(yreduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, tmpx, Hf, Wf, H, sy, total, dz_lo);
-      RHSEG_LAUNCH_CHECK();
-      return RHSEG_OK;
+#undef RHSEG_DZB_V
+#undef RHSEG_DZB
+      if (rc != RHSEG_OK) return rc;
+      if (done) return RHSEG_OK;
     }
   }
+  // generic: shared-memory tiled kernel (any alignment, halo recomputation); writes dz_lo
   const int ry_max = region_extent(ADJ_TH, sy, H), rx_max = region_extent(ADJ_TW, sx, W) | 1;  // odd pitch: fewer bank conflicts
   const size_t smem = ((size_t)K * ry_max * rx_max + (size_t)K * ry_max * ADJ_TW) * sizeof(float);
   if (smem > 200 * 1024) return RHSEG_ERR_UNSUPPORTED;  // upsampling factor too large for the tiled kernel
@@ -581,7 +700,8 @@ extern "C" int rhseg_upsample_adjoint(const float* dz_hi, int B, int K, int Hf, 
   if (!dz_hi || !dz_lo || B <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   FusedDzArgs fa{};
-  RHSEG_DISPATCH_K(K, return (launch_adjoint<KK, 0, 0>(dz_hi, fa, B, Hf, Wf, H, W, dz_lo, tmp, (flags & RHSEG_DZ_PREZEROED) != 0, (cudaStream_t)stream)));
+  (void)tmp;  // workspace of an earlier two-kernel form; unused
+  RHSEG_DISPATCH_K(K, return (launch_adjoint<KK, 0, 0>(dz_hi, fa, 0, B, Hf, Wf, H, W, dz_lo, (flags & RHSEG_DZ_PREZEROED) != 0, (cudaStream_t)stream)));
   return RHSEG_OK;
 }
 
@@ -593,15 +713,18 @@ extern "C" int rhseg_head_dz_lowres_fused(const float* logits, const float* targ
                                           float* dp_prev, float* tmp, int flags, void* stream) {
   if (!logits || !targets || !coef || !dz_lo || B <= 0 || Hf <= 0 || Wf <= 0 || H <= 0 || W <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  const int hint = RHSEG_GROUP_HINT_OF(act_mode);
+  act_mode &= 0xff;
+  (void)tmp;  // workspace of an earlier two-kernel form; unused
   if (act_mode == RHSEG_ACT_GROUPED && (!prev_probs || !table)) return RHSEG_ERR_ARG;
   FusedDzArgs fa{logits, targets, t_bstride, t_cstride, coef, g_ce, g_dice, prev_probs, table, g_uniform,
                  (float)inv_npix, dp_pix, pix_mask, dp_prev, K_prev};
   cudaStream_t st = (cudaStream_t)stream;
   const bool pz = (flags & RHSEG_DZ_PREZEROED) != 0;
   RHSEG_DISPATCH_K(K, {
-    if (act_mode == RHSEG_ACT_SIGMOID) return launch_adjoint<KK, 1, RHSEG_ACT_SIGMOID>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, pz, st);
-    if (act_mode == RHSEG_ACT_GROUPED) return launch_adjoint<KK, 1, RHSEG_ACT_GROUPED>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, pz, st);
-    return launch_adjoint<KK, 1, RHSEG_ACT_ZEROS>(nullptr, fa, B, Hf, Wf, H, W, dz_lo, tmp, pz, st);
+    if (act_mode == RHSEG_ACT_SIGMOID) return launch_adjoint<KK, 1, RHSEG_ACT_SIGMOID>(nullptr, fa, hint, B, Hf, Wf, H, W, dz_lo, pz, st);
+    if (act_mode == RHSEG_ACT_GROUPED) return launch_adjoint<KK, 1, RHSEG_ACT_GROUPED>(nullptr, fa, hint, B, Hf, Wf, H, W, dz_lo, pz, st);
+    return launch_adjoint<KK, 1, RHSEG_ACT_ZEROS>(nullptr, fa, hint, B, Hf, Wf, H, W, dz_lo, pz, st);
   });
   return RHSEG_OK;
 }
@@ -614,6 +737,7 @@ extern "C" int rhseg_head_dz_fullres_fused(const float* logits, const float* tar
                                            void* stream) {
   if (!logits || !targets || !coef || !dz_out || B <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  act_mode &= 0xff;
   if (act_mode == RHSEG_ACT_GROUPED && (!prev_probs || !table)) return RHSEG_ERR_ARG;
   FusedDzArgs fa{logits, targets, t_bstride, t_cstride, coef, g_ce, g_dice, prev_probs, table, g_uniform,
                  (float)inv_npix, dp_pix, pix_mask, dp_prev, K_prev};

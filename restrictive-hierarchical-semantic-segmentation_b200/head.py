@@ -96,6 +96,7 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words
             z_lo = zlo_all[zlo_off:zlo_off + B * K * Hf * Wf].view(B, K, Hf, Wf)
             zlo_off += B * K * Hf * Wf
         ev = evaluate(L, (B, C, Hf, Wf, H, W), workspace) if evaluate is not None else None
+        hint = tree.group_hint(L)  # uniform group size: kernels with the group layout fixed at compile time
         # The evaluation of level L only needs its logits (and the previous level's index map): for all
         # but the last level it runs on a side stream, overlapping the (memory-bound) forward of the next
         # level; the last level's evaluation is fused into its hi-res forward kernel when there is one.
@@ -107,12 +108,12 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words
                 used_side = False
             call("rhseg_head_level_fwd_eval", ptr(f), ptr(eff_w), ptr(eff_b),
                  ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
-                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum),
+                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L] | hint, ptr(z_lo), ptr(z), ptr(p), ptr(psum),
                  t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, words_ptr, idx_ptr, 1 | 2, st)
         else:
             call("rhseg_head_level_fwd", ptr(f), ptr(eff_w), ptr(eff_b),
                  ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
-                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L], ptr(z_lo), ptr(z), ptr(p), ptr(psum), 2 if upsampled else 0, st)
+                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L] | hint, ptr(z_lo), ptr(z), ptr(p), ptr(psum), 2 if upsampled else 0, st)
             if ev is not None:
                 t_ptr, t_bs, t_cs, pt_ptr, pidx_ptr, words_ptr, idx_ptr = ev
                 if overlap:
@@ -120,14 +121,14 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words
                     side = _side_stream(dev)
                     side.wait_stream(main)  # logits of this level (and everything before) are ready
                     call("rhseg_level_eval", ptr(z), t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, ptr(tables[L]),
-                         B, K, n_pix, 1 if L > 0 else 0, words_ptr, idx_ptr, 1, side.cuda_stream)
+                         B, K, n_pix, (1 if L > 0 else 0) | hint, words_ptr, idx_ptr, 1, side.cuda_stream)
                     used_side = True
                 else:
                     if used_side:  # the previous level's index map is produced on the side stream
                         torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
                         used_side = False
                     call("rhseg_level_eval", ptr(z), t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, ptr(tables[L]),
-                         B, K, n_pix, 1 if L > 0 else 0, words_ptr, idx_ptr, 1, st)
+                         B, K, n_pix, (1 if L > 0 else 0) | hint, words_ptr, idx_ptr, 1, st)
         probs.append(p); logits.append(z); psums.append(psum); eff_ws.append(eff_w); gbs.append(gb)
     if used_side:
         torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))

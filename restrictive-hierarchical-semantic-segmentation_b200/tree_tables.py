@@ -98,6 +98,15 @@ class ClassTree:
     def group_count(self, L):
         return 0 if L == 0 else len(self.child_groups[L - 1])
 
+    def group_hint(self, L):
+        """RHSEG_GROUP_HINT bits of level L: the common size of its parent groups (the reference's trees: one group of
+        4 / 2 / 3 channels, or two groups of 2), 0 when the sizes differ or the level has no group.  OR-ed into the
+        act_mode / child arguments, it selects kernels with the group layout fixed at compile time."""
+        if L == 0 or not self.child_groups[L - 1]:
+            return 0
+        sizes = {len(kids) for _, kids in self.child_groups[L - 1]}
+        return (sizes.pop() << 8) if len(sizes) == 1 else 0
+
     # ---- flat -> hierarchy stitching tables (predictEval.py:36-83) ----
     def bfs_names(self):
         """Breadth-first node order (predictEval.bfs_order): the channel order of class_map.csv."""
