@@ -230,7 +230,7 @@ def run_ours(args, rank, world, local_rank):
 
     def counting_call(name, *a):
         counted["n"] += kernels_per_call(name, upsampled)
-        if timing_on["v"] and name == "rhseg_head_conv_bwd":
+        if timing_on["v"] and name in ("rhseg_head_conv_bwd", "rhseg_head_conv_bwd_params"):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             raw_call(name, *a)

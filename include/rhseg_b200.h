@@ -111,7 +111,9 @@ int rhseg_head_level_fwd(const float* feats, const float* eff_w, const float* ef
                          float* z_lo, float* logits, float* probs, double* psum, int zero_psum,
                          void* stream);
 /* zero_psum bit 1 (value 2): z_lo was zeroed by the caller (one fill for all levels); without it the
- * low-res pass zeroes z_lo itself whenever pixel tiles are split between CTAs.               */
+ * low-res pass zeroes z_lo itself whenever pixel tiles are split between CTAs.
+ * zero_psum bit 2 (value 4): eff_w / eff_b are ONE [K,C] / [K] pair shared by all samples (a level without
+ * FiLM, i.e. level 0: pass the head's own weight and bias, no rhseg_film_fold launch).       */
 
 /* Level forward of an UPSAMPLED head (HRNet) fused with rhseg_level_eval: the hi-res pass that
  * interpolates and activates the logits also evaluates them against the ternary targets while
@@ -170,10 +172,24 @@ int rhseg_head_dz_lowres_fused(const float* logits, const float* targets, long t
 /* 1x1 conv backward at feature resolution: dfeats[b,c,n] = sum_k eff_w[b,k,c] dz[b,k,n];
  * S[b,k,c] = sum_n dz[b,k,n] feats[b,c,n]; s[b,k] = sum_n dz[b,k,n]  (fp64, accumulated with
  * atomics: zeroed here when zero_sums != 0, otherwise the caller passes zeroed buffers).
- * dfeats may be NULL (features do not require grad).                                      */
+ * dfeats may be NULL (features do not require grad).
+ * zero_sums bit 0: zero S / s here; bit 1 (value 2): eff_w is one [K,C] matrix shared by all samples.  */
 int rhseg_head_conv_bwd(const float* feats, const float* dz, const float* eff_w,
                         int B, int C, int K, int n_pix,
                         float* dfeats, double* S, double* s, int zero_sums, void* stream);
+
+/* rhseg_head_conv_bwd followed by rhseg_head_param_grads in ONE launch: the last CTA to finish forms the parameter
+ * gradients from the complete sums (no second kernel on the level chain).  Arguments: those of the two functions;
+ * flags = zero_sums of rhseg_head_conv_bwd | 4 when g_prev is zero on entry (part of a larger zero fill; otherwise it is
+ * zeroed here); n_pix_out = H*W of the output (the FiLM pool size); ticket = a device counter that is zero on entry (left
+ * zero).  Two forms, same results: conv kernel + 12-CTA parameter kernel behind a programmatic dependent launch
+ * (default, measured faster for C = 720), or the parameter gradients as the tail of the conv kernel's last CTA
+ * (RHSEG_PARAM_TAIL=1).                                                                                        */
+int rhseg_head_conv_bwd_params(const float* feats, const float* dz, const float* eff_w, int B, int C, int K,
+                               int n_pix, float* dfeats, double* S, double* s, int flags, const float* head_w,
+                               const float* film_w, const float* gamma_beta, const double* prev_psum,
+                               double n_pix_out, int K_prev, float* d_head_w, float* d_head_b, float* d_film_w,
+                               float* d_film_b, double* g_prev, unsigned* ticket, void* stream);
 
 /* Parameter gradients of one level from S / s (all sums over the batch):
  *   d_head_w [K,C], d_head_b [K]; and when film_w != NULL: d_film_w [2C,K_prev],
@@ -283,7 +299,8 @@ int rhseg_step_finalize(const void* eval_words, const float* weights_all, int B,
  *   out_words (8-byte words, zeroed here):
  *     [B*K*RHSEG_NSTAT fp64 statistics][RHSEG_MAX_K fp64 consistency sums][nc*nc int64 confusion]
  *   idx_out: uint8 [B,n_pix] prediction index map (NULL when no deeper level needs it).
- *   flags: RHSEG_EVAL_PREZEROED = the caller already zeroed out_words (one fill for all levels). */
+ *   flags: RHSEG_EVAL_PREZEROED = the caller already zeroed out_words (one fill for all levels).
+ *   child: 0 / 1, optionally | RHSEG_GROUP_HINT(gsz).                                          */
 int rhseg_level_eval(const float* logits, const float* targets, long t_bstride, long t_cstride,
                      const float* parent_targets, long pt_bstride, long pt_cstride,
                      const unsigned char* prev_idx, const int32_t* table, int B, int K, int n_pix,

@@ -102,11 +102,110 @@ act_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ prev_
 // (KP-1 + 5-log2(KP) shuffles).  The per-channel sums of the current (sample, stage) segment
 // stay in registers across tiles and leave the warp as fp64 atomics when the segment ends.
 // ------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------
+// Parameter gradients as the TAIL of the conv backward (no second launch, no launch gap on the level chain):
+// every CTA takes a ticket when its share of S / s has been added; the last one forms, from the complete sums,
+//   d_head_w = sum_b (S_b diag(gamma_b) + s_b beta_b^T),  d_head_b = sum_b s_b,
+//   dgamma_b[c] = sum_k S_b[k,c] W[k,c],  dbeta_b = W^T s_b,  d_film_w = sum_b [dgamma|dbeta]_b cond_b^T,
+//   d_film_b = sum_b [dgamma|dbeta]_b,  g_prev[b] = film_w^T [dgamma|dbeta]_b
+// (closed forms: DESIGN.md 3.5).  Same arguments as rhseg_head_param_grads; all sums in fp64.
+// ------------------------------------------------------------------------------------
+struct ParamTail {
+  unsigned* ticket;  // device counter, zero on entry, left zero; nullptr = no tail
+  const float* head_w;
+  const float* film_w;
+  const float* gamma_beta;
+  const double* prev_psum;
+  double n_pix;
+  int B, K_prev;
+  float* d_head_w;
+  float* d_head_b;
+  float* d_film_w;
+  float* d_film_b;
+  double* g_prev;
+};
+
+template <int K>
+__device__ __noinline__ void param_grads_tail(const ParamTail& pt, const double* __restrict__ S, const double* __restrict__ s, int C,
+                                              double* sm /* shared: B*K_prev + 2*B*C doubles */, int tid, int nthr) {
+  const int B = pt.B, Kp = pt.film_w ? pt.K_prev : 0;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  double* cond = sm;                    // [B][Kp]  pooled probabilities of the previous level (fp32 values, as in the forward)
+  double* dg = sm + (size_t)B * Kp;     // [B][C]   dgamma
+  double* db = dg + (size_t)B * C;      // [B][C]   dbeta
+  for (int i = tid; i < B * Kp; i += nthr) cond[i] = (double)(float)fast_div(pt.prev_psum[i], pt.n_pix);
+  consumer_sync(nthr);
+  // phase 1: thread <-> channel; every load of a channel is independent of the others (no barrier inside)
+  for (int c = tid; c < C; c += nthr) {
+    float w[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) w[k] = pt.head_w[(size_t)k * C + c];
+    double dw[K], dfb_g = 0.0, dfb_b = 0.0, dfw_g[RHSEG_MAX_K], dfw_b[RHSEG_MAX_K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) dw[k] = 0.0;
+#pragma unroll
+    for (int j = 0; j < RHSEG_MAX_K; ++j) { dfw_g[j] = 0.0; dfw_b[j] = 0.0; }
+    for (int b = 0; b < B; ++b) {
+      const double gam = Kp ? (double)pt.gamma_beta[(size_t)b * 2 * C + c] : 1.0;
+      const double bet = Kp ? (double)pt.gamma_beta[(size_t)b * 2 * C + C + c] : 0.0;
+      double dgam = 0.0, dbet = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double Sv = __ldcg(S + ((size_t)b * K + k) * C + c);  // accumulated by other CTAs' atomics: read at L2
+        const double sv = __ldcg(s + b * K + k);
+        dw[k] += Sv * gam + sv * bet;
+        dgam += Sv * (double)w[k];
+        dbet += (double)w[k] * sv;
+      }
+      if (Kp) {
+        dfb_g += dgam;
+        dfb_b += dbet;
+        dg[(size_t)b * C + c] = dgam;
+        db[(size_t)b * C + c] = dbet;
+#pragma unroll
+        for (int j = 0; j < RHSEG_MAX_K; ++j)
+          if (j < Kp) {
+            dfw_g[j] += dgam * cond[b * Kp + j];
+            dfw_b[j] += dbet * cond[b * Kp + j];
+          }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) pt.d_head_w[(size_t)k * C + c] = (float)dw[k];
+    if (Kp) {
+      pt.d_film_b[c] = (float)dfb_g;
+      pt.d_film_b[C + c] = (float)dfb_b;
+#pragma unroll
+      for (int j = 0; j < RHSEG_MAX_K; ++j)
+        if (j < Kp) {
+          pt.d_film_w[(size_t)c * Kp + j] = (float)dfw_g[j];
+          pt.d_film_w[(size_t)(C + c) * Kp + j] = (float)dfw_b[j];
+        }
+    }
+  }
+  if (tid < K) {
+    double acc = 0.0;
+    for (int b = 0; b < B; ++b) acc += __ldcg(s + b * K + tid);
+    pt.d_head_b[tid] = (float)acc;
+  }
+  if (Kp == 0) return;
+  consumer_sync(nthr);
+  // phase 2: g_prev[b][j] = sum_c film_w[c][j] dgamma[b][c] + film_w[C+c][j] dbeta[b][c]: one warp per (b, j) pair
+  for (int p = warp; p < B * Kp; p += nwarp) {
+    const int b = p / Kp, j = p - b * Kp;
+    double acc = 0.0;
+    for (int c = lane; c < C; c += 32)
+      acc += (double)pt.film_w[(size_t)c * Kp + j] * dg[(size_t)b * C + c] + (double)pt.film_w[(size_t)(C + c) * Kp + j] * db[(size_t)b * C + c];
+    acc = warp_sum(acc);
+    if (lane == 0) pt.g_prev[p] = acc;
+  }
+}
+
 template <int K, int VEC, int J, typename CFG>
 __global__ void __launch_bounds__(CFG::THREADS)
 conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, const float* __restrict__ eff_w,
-                int C, int N, int n_tiles, int n_stages, long units_total, int a0, float* __restrict__ dfeats,
-                double* __restrict__ S, double* __restrict__ s) {
+                int C, int N, int n_tiles, int n_stages, long units_total, int a0, int w_shared, float* __restrict__ dfeats,
+                double* __restrict__ S, double* __restrict__ s, ParamTail pt) {
   pdl_wait();
   constexpr int KP = pad_k(K);
   constexpr int P = J * VEC;
@@ -229,7 +328,7 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
         __syncwarp();
         for (int e = lane; e < CH * KP; e += 32) {
           const int cc = e / KP, k = e - cc * KP;
-          w_s[e] = (cc < ccnt && k < K) ? __ldg(eff_w + ((size_t)b * K + k) * C + c0 + cc) : 0.f;
+          w_s[e] = (cc < ccnt && k < K) ? __ldg(eff_w + ((size_t)(w_shared ? 0 : b) * K + k) * C + c0 + cc) : 0.f;
         }
         __syncwarp();
       }
@@ -348,11 +447,25 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
     advance();
   }
   if (cur_seg >= 0) flush();
+  if (pt.ticket != nullptr) {
+    // last CTA done: S / s are complete -> parameter gradients (the ring is free: its memory holds the pool-gradient sums)
+    __shared__ int is_last;
+    __threadfence();
+    consumer_sync(NCONS);
+    if (tid == 0) is_last = (atomicAdd(pt.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    consumer_sync(NCONS);
+    if (is_last) {
+      __threadfence();
+      param_grads_tail<K>(pt, S, s, C, reinterpret_cast<double*>(ring), tid, NCONS);
+      if (tid == 0) *pt.ticket = 0u;  // ready for the next launch / graph replay
+    }
+  }
 }
 
 template <int K, int VEC, int J, typename CFG>
 static int launch_conv_bwd(const float* feats, const float* dz, const float* eff_w, int B, int C, int N,
-                           float* dfeats, double* S, double* s, int sm_count, cudaStream_t st) {
+                           float* dfeats, double* S, double* s, int sm_count, cudaStream_t st, int w_shared,
+                           const ParamTail& pt) {
   constexpr int KP = pad_k(K);
   constexpr int T = CFG::CONSUMERS * J * VEC;
   const size_t smem = 128 + ((size_t)CFG::NS * CFG::CH * (T + 4) + (size_t)CFG::NCW * CFG::CH * KP) * sizeof(float);
@@ -366,7 +479,7 @@ static int launch_conv_bwd(const float* feats, const float* dz, const float* eff
   const long units_total = (long)B * n_stages * n_tiles;
   const long grid = std::max<long>(1, std::min<long>((long)sm_count * per_sm, units_total));
   const int a0 = (int)((reinterpret_cast<uintptr_t>(feats) >> 2) & 3);
-  launch_pdl(kern, dim3((unsigned)grid), dim3(CFG::THREADS), smem, st, feats, dz, eff_w, C, N, n_tiles, n_stages, units_total, a0, dfeats, S, s);
+  launch_pdl(kern, dim3((unsigned)grid), dim3(CFG::THREADS), smem, st, feats, dz, eff_w, C, N, n_tiles, n_stages, units_total, a0, w_shared, dfeats, S, s, pt);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }
@@ -516,12 +629,13 @@ extern "C" int rhseg_head_act_bwd(const float* logits, const float* prev_probs, 
   return RHSEG_OK;
 }
 
-extern "C" int rhseg_head_conv_bwd(const float* feats, const float* dz, const float* eff_w, int B, int C, int K,
-                                   int n_pix, float* dfeats, double* S, double* s, int zero_sums, void* stream) {
+static int conv_bwd_impl(const float* feats, const float* dz, const float* eff_w, int B, int C, int K, int n_pix,
+                         float* dfeats, double* S, double* s, int zero_sums, void* stream, const ParamTail& pt) {
   if (!feats || !dz || !eff_w || !S || !s || B <= 0 || C <= 0 || n_pix <= 0) return RHSEG_ERR_ARG;
   if (K < 1 || K > RHSEG_KERNEL_MAX_K) return RHSEG_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  if (zero_sums) {
+  const int w_shared = (zero_sums & 2) ? 1 : 0;
+  if (zero_sums & 1) {
     RHSEG_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * (size_t)B * K * C, st));
     RHSEG_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * (size_t)B * K, st));
   }
@@ -532,21 +646,54 @@ extern "C" int rhseg_head_conv_bwd(const float* feats, const float* dz, const fl
     if (v4) {
       if constexpr (KK == 4) {
         const int t = tune_env("RHSEG_TUNE_BWD_V4");
-        if (t == 1) return launch_conv_bwd<KK, 4, 1, PipeCfg<4, 8, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
-        if (t == 2) return launch_conv_bwd<KK, 4, 1, PipeCfg<8, 16, 2>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
-        if (t == 3) return launch_conv_bwd<KK, 4, 1, PipeCfg<8, 16, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+        if (t == 1) return launch_conv_bwd<KK, 4, 1, PipeCfg<4, 8, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st, w_shared, pt);
+        if (t == 2) return launch_conv_bwd<KK, 4, 1, PipeCfg<8, 16, 2>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st, w_shared, pt);
+        if (t == 3) return launch_conv_bwd<KK, 4, 1, PipeCfg<8, 16, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st, w_shared, pt);
       }
-      return launch_conv_bwd<KK, 4, 1, BwdCfgV4>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+      return launch_conv_bwd<KK, 4, 1, BwdCfgV4>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st, w_shared, pt);
     }
     if constexpr (KK == 4) {
       const int t = tune_env("RHSEG_TUNE_BWD_S1");
-      if (t == 1) return launch_conv_bwd<KK, 1, 4, PipeCfg<8, 16, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
-      if (t == 2) return launch_conv_bwd<KK, 1, 4, PipeCfg<8, 24, 2>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
-      if (t == 3) return launch_conv_bwd<KK, 1, 4, PipeCfg<8, 16, 2>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+      if (t == 1) return launch_conv_bwd<KK, 1, 4, PipeCfg<8, 16, 3>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st, w_shared, pt);
+      if (t == 2) return launch_conv_bwd<KK, 1, 4, PipeCfg<8, 24, 2>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st, w_shared, pt);
+      if (t == 3) return launch_conv_bwd<KK, 1, 4, PipeCfg<8, 16, 2>>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st, w_shared, pt);
     }
-    return launch_conv_bwd<KK, 1, (KK <= 4 ? 4 : 2), BwdCfgS1>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st);
+    return launch_conv_bwd<KK, 1, (KK <= 4 ? 4 : 2), BwdCfgS1>(feats, dz, eff_w, B, C, n_pix, dfeats, S, s, sms, st, w_shared, pt);
   });
   return RHSEG_OK;
+}
+
+extern "C" int rhseg_head_conv_bwd(const float* feats, const float* dz, const float* eff_w, int B, int C, int K,
+                                   int n_pix, float* dfeats, double* S, double* s, int zero_sums, void* stream) {
+  ParamTail none{};
+  return conv_bwd_impl(feats, dz, eff_w, B, C, K, n_pix, dfeats, S, s, zero_sums, stream, none);
+}
+
+extern "C" int rhseg_head_conv_bwd_params(const float* feats, const float* dz, const float* eff_w, int B, int C, int K,
+                                          int n_pix, float* dfeats, double* S, double* s, int flags, const float* head_w,
+                                          const float* film_w, const float* gamma_beta, const double* prev_psum,
+                                          double n_pix_out, int K_prev, float* d_head_w, float* d_head_b, float* d_film_w,
+                                          float* d_film_b, double* g_prev, unsigned* ticket, void* stream) {
+  if (!head_w || !d_head_w || !d_head_b || !ticket) return RHSEG_ERR_ARG;
+  if (film_w) {
+    if (!gamma_beta || !prev_psum || !d_film_w || !d_film_b || !g_prev || n_pix_out <= 0) return RHSEG_ERR_ARG;
+    if (K_prev < 1 || K_prev > RHSEG_MAX_K) return RHSEG_ERR_UNSUPPORTED;
+  }
+  // Measured (HRNet-W48 tl, B = 4): the single-CTA tail costs 25 us per launch against 8.6 us for the 12-CTA
+  // rhseg_head_param_grads kernel behind a programmatic dependent launch, so the two-kernel form is the default;
+  // RHSEG_PARAM_TAIL=1 selects the tail (kept for small C / B where one CTA is enough).
+  static int use_tail = -1;
+  if (use_tail < 0) { const char* e = getenv("RHSEG_PARAM_TAIL"); use_tail = (e && e[0] == '1') ? 1 : 0; }
+  if (!use_tail || (film_w && ((long)B * K_prev + 2L * B * C) * 8 > 60 * 1024)) {
+    ParamTail none{};
+    const int rc = conv_bwd_impl(feats, dz, eff_w, B, C, K, n_pix, dfeats, S, s, flags, stream, none);
+    if (rc != RHSEG_OK) return rc;
+    // g_prev: the caller's buffer is zero on entry when bit 2 (value 4) of flags is set (part of a larger zero fill)
+    return rhseg_head_param_grads(S, s, head_w, film_w, gamma_beta, prev_psum, n_pix_out, B, C, K, K_prev, d_head_w, d_head_b,
+                                  d_film_w, d_film_b, g_prev, (flags & 4) ? 1 : 0, stream);
+  }
+  ParamTail pt{ticket, head_w, film_w, gamma_beta, prev_psum, n_pix_out, B, K_prev, d_head_w, d_head_b, d_film_w, d_film_b, g_prev};
+  return conv_bwd_impl(feats, dz, eff_w, B, C, K, n_pix, dfeats, S, s, flags, stream, pt);
 }
 
 extern "C" int rhseg_head_param_grads(const double* S, const double* s, const float* head_w, const float* film_w,

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(CFG::THREADS)
 head_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ eff_w,
                 const float* __restrict__ eff_b, const float* __restrict__ prev_probs,
                 const int32_t* __restrict__ table, int C, int N, int K_prev, int n_tiles, int n_stages,
-                long units_total, int a0, float* __restrict__ logits, float* __restrict__ probs,
+                long units_total, int a0, int w_shared, float* __restrict__ logits, float* __restrict__ probs,
                 double* __restrict__ psum) {
   pdl_wait();
   constexpr int KP = pad_k(K);
@@ -186,14 +186,14 @@ head_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ eff_w
           }
         }
         csync();
-        const float* wsrc = eff_w + (size_t)b * K * C;
+        const float* wsrc = w_shared ? eff_w : eff_w + (size_t)b * K * C;  // level 0: the head's own [K,C] weights
         for (int k = 0; k < K; ++k)
           for (int c = tid; c < C; c += NCONS) w_t[c * KP + k] = wsrc[(size_t)k * C + c];
         if constexpr (KP > K)
           for (int k = K; k < KP; ++k)
             for (int c = tid; c < C; c += NCONS) w_t[c * KP + k] = 0.f;
 #pragma unroll
-        for (int k = 0; k < K; ++k) bias[k] = eff_b[b * K + k];
+        for (int k = 0; k < K; ++k) bias[k] = eff_b[(w_shared ? 0 : b * K) + k];
         cur_b = b;
         csync();
       }
@@ -342,7 +342,7 @@ head_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ eff_w
 template <int K, int VEC, int J, int MODE, typename CFG>
 static int launch_fwd(const float* feats, const float* eff_w, const float* eff_b, const float* prev_probs,
                       const int32_t* table, int B, int C, int N, int K_prev, float* logits, float* probs,
-                      double* psum, cudaStream_t st, bool out_prezeroed = false) {
+                      double* psum, cudaStream_t st, bool out_prezeroed = false, int w_shared = 0) {
   constexpr int KP = pad_k(K);
   constexpr int T = CFG::CONSUMERS * J * VEC;
   const size_t smem = 128 + ((size_t)CFG::NS * CFG::CH * (T + 4) + (size_t)C * KP + CFG::NCW * K) * sizeof(float);
@@ -362,7 +362,7 @@ static int launch_fwd(const float* feats, const float* eff_w, const float* eff_b
     RHSEG_CUDA(cudaMemsetAsync(logits, 0, sizeof(float) * (size_t)B * K * N, st));
   const int a0 = (int)((reinterpret_cast<uintptr_t>(feats) >> 2) & 3);
   launch_pdl(kern, dim3((unsigned)grid), dim3(CFG::THREADS), smem, st, feats, eff_w, eff_b, prev_probs, table, C, N, K_prev, n_tiles, n_stages,
-                                                  units_total, a0, logits, probs, psum);
+                                                  units_total, a0, w_shared, logits, probs, psum);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }
@@ -381,18 +381,18 @@ using FwdCfgS1 = PipeCfg<4, 16, 4, 2>;  // scalar rows, T = 128*J px, two produc
 template <int K, int MODE>
 static int fwd_fullres(const float* feats, const float* eff_w, const float* eff_b, const float* prev_probs,
                        const int32_t* table, int B, int C, int N, int K_prev, float* logits, float* probs,
-                       double* psum, cudaStream_t st) {
+                       double* psum, cudaStream_t st, int w_shared) {
   const bool v4 = rows_vec4(feats, N) && rows_vec4(logits, N) && rows_vec4(probs, N) && (!prev_probs || rows_vec4(prev_probs, N));
   if (v4) {
     if constexpr (K == 4) {
       const int t = tune_env("RHSEG_TUNE_FWD_V4");
-      if (t == 1) return launch_fwd<K, 4, 1, MODE, PipeCfg<4, 8, 4>>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st);
-      if (t == 2) return launch_fwd<K, 4, 1, MODE, PipeCfg<8, 16, 2>>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st);
-      if (t == 3) return launch_fwd<K, 4, 1, MODE, PipeCfg<8, 16, 3>>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st);
+      if (t == 1) return launch_fwd<K, 4, 1, MODE, PipeCfg<4, 8, 4>>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st, false, w_shared);
+      if (t == 2) return launch_fwd<K, 4, 1, MODE, PipeCfg<8, 16, 2>>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st, false, w_shared);
+      if (t == 3) return launch_fwd<K, 4, 1, MODE, PipeCfg<8, 16, 3>>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st, false, w_shared);
     }
-    return launch_fwd<K, 4, 1, MODE, FwdCfgV4>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st);
+    return launch_fwd<K, 4, 1, MODE, FwdCfgV4>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st, false, w_shared);
   }
-  return launch_fwd<K, 1, 2, MODE, FwdCfgS1>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st);
+  return launch_fwd<K, 1, 2, MODE, FwdCfgS1>(feats, eff_w, eff_b, prev_probs, table, B, C, N, K_prev, logits, probs, psum, st, false, w_shared);
 }
 
 }  // namespace rhseg
@@ -430,6 +430,7 @@ static int level_fwd_impl(const float* feats, const float* eff_w, const float* e
   cudaStream_t st = (cudaStream_t)stream;
   if (zero_psum & 1) RHSEG_CUDA(cudaMemsetAsync(psum, 0, sizeof(double) * B * K, st));
   const bool zlo_zeroed = (zero_psum & 2) != 0;
+  const int w_shared = (zero_psum & 4) ? 1 : 0;
   const bool up = (H != Hf) || (W != Wf);
   if (ea && !up) return RHSEG_ERR_UNSUPPORTED;
   if (act_mode == RHSEG_ACT_GROUPED && table == nullptr) return RHSEG_ERR_ARG;
@@ -437,27 +438,27 @@ static int level_fwd_impl(const float* feats, const float* eff_w, const float* e
   if (!up) {
     RHSEG_DISPATCH_K(K, {
       if (act_mode == RHSEG_ACT_SIGMOID)
-        return fwd_fullres<KK, RHSEG_ACT_SIGMOID>(feats, eff_w, eff_b, prev_probs, table, B, C, Nf, K_prev, logits, probs, psum, st);
+        return fwd_fullres<KK, RHSEG_ACT_SIGMOID>(feats, eff_w, eff_b, prev_probs, table, B, C, Nf, K_prev, logits, probs, psum, st, w_shared);
       if (act_mode == RHSEG_ACT_GROUPED)
-        return fwd_fullres<KK, RHSEG_ACT_GROUPED>(feats, eff_w, eff_b, prev_probs, table, B, C, Nf, K_prev, logits, probs, psum, st);
-      return fwd_fullres<KK, RHSEG_ACT_ZEROS>(feats, eff_w, eff_b, prev_probs, table, B, C, Nf, K_prev, logits, probs, psum, st);
+        return fwd_fullres<KK, RHSEG_ACT_GROUPED>(feats, eff_w, eff_b, prev_probs, table, B, C, Nf, K_prev, logits, probs, psum, st, w_shared);
+      return fwd_fullres<KK, RHSEG_ACT_ZEROS>(feats, eff_w, eff_b, prev_probs, table, B, C, Nf, K_prev, logits, probs, psum, st, w_shared);
     });
   }
   if (!z_lo) return RHSEG_ERR_ARG;
   RHSEG_DISPATCH_K(K, {
     int rc;
     if (rows_vec4(feats, Nf) && rows_vec4(z_lo, Nf)) {
-      rc = launch_fwd<KK, 4, 1, MODE_CONV_ONLY, FwdCfgV4>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, zlo_zeroed);
+      rc = launch_fwd<KK, 4, 1, MODE_CONV_ONLY, FwdCfgV4>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, zlo_zeroed, w_shared);
     } else {
       int t = 0;
       if constexpr (KK == 4) t = tune_env("RHSEG_TUNE_FWD_S1");
       if constexpr (KK == 4) {
-        if (t == 1) rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, PipeCfg<8, 16, 3, 2>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
-        else if (t == 2) rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, PipeCfg<8, 8, 4, 2>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
-        else if (t == 3) rc = launch_fwd<KK, 1, 4, MODE_CONV_ONLY, PipeCfg<4, 16, 4, 1>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st);
-        else rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, FwdCfgS1>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, zlo_zeroed);
+        if (t == 1) rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, PipeCfg<8, 16, 3, 2>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, false, w_shared);
+        else if (t == 2) rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, PipeCfg<8, 8, 4, 2>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, false, w_shared);
+        else if (t == 3) rc = launch_fwd<KK, 1, 4, MODE_CONV_ONLY, PipeCfg<4, 16, 4, 1>>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, false, w_shared);
+        else rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, FwdCfgS1>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, zlo_zeroed, w_shared);
       } else {
-        rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, FwdCfgS1>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, zlo_zeroed);
+        rc = launch_fwd<KK, 1, 2, MODE_CONV_ONLY, FwdCfgS1>(feats, eff_w, eff_b, nullptr, nullptr, B, C, Nf, K_prev, z_lo, nullptr, nullptr, st, zlo_zeroed, w_shared);
       }
     }
     if (rc != RHSEG_OK) return rc;
@@ -495,7 +496,7 @@ extern "C" int rhseg_head_level_fwd_eval(const float* feats, const float* eff_w,
               reinterpret_cast<unsigned long long*>(cons + RHSEG_MAX_K), idx_out};
   bool need_eval = false;
   const int rc = level_fwd_impl(feats, eff_w, eff_b, prev_probs, table, B, C, Hf, Wf, H, W, K, K_prev, act_mode, z_lo, logits,
-                                probs, psum, (flags & 2), stream, &ea, &need_eval);
+                                probs, psum, (flags & (2 | 4)), stream, &ea, &need_eval);
   if (rc != RHSEG_OK || !need_eval) return rc;
   // shapes the band kernel does not take: the evaluation runs as its own kernel on the finished logits
   return rhseg_level_eval(logits, targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, table, B, K,

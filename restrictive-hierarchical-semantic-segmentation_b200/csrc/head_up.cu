@@ -273,7 +273,7 @@ upsample_band_kernel(const float* __restrict__ z_lo, const float* __restrict__ p
           if (g < gr.n) {
             const Vec<VEC> pv = *reinterpret_cast<const Vec<VEC>*>(sf + (size_t)(row++) * W);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) ppg[g][v] = ok ? pv.v[v] : 0.f;
+            for (int v = 0; v < VEC; ++v) ppg[g][v] = pv.v[v];
           } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) ppg[g][v] = 0.f;
@@ -440,6 +440,9 @@ static int launch_band(const float* z_lo, const float* prev_probs, const int32_t
   RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(smem_for(H), 200 * 1024)));
   RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ncons + 32, smem0));
   if (per_sm < 1) return RHSEG_OK;
+  static int tune_ctas = -1;
+  if (tune_ctas < 0) { const char* e = getenv("RHSEG_TUNE_UP_CTAS"); tune_ctas = e ? atoi(e) : 0; }
+  if (tune_ctas > 0) per_sm = std::min(per_sm, tune_ctas);
   const long slots = std::max<long>(1, (long)per_sm * device_sm_count() / B);
   int band = std::max(4, (int)((H + slots - 1) / slots));
   while (band > 4 && smem_for(band) > 200 * 1024) --band;
@@ -485,7 +488,9 @@ static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32
 #define RHSEG_BAND(VEC, EK, GS) rc = launch_band<K, VEC, MODE, EK, GS>(z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, sy, sx, logits, probs, psum, st, e, &done)
 #define RHSEG_BAND_V(EK, GS)                                  \
       do {                                                    \
-        if (v4) RHSEG_BAND(4, EK, GS);                        \
+        if constexpr (K <= 4) {                               \
+          if (v4) RHSEG_BAND(4, EK, GS);                      \
+        }                                                     \
         if (!done && rc == RHSEG_OK && v2) RHSEG_BAND(2, EK, GS); \
       } while (0)
       if constexpr (MODE == RHSEG_ACT_SIGMOID) {

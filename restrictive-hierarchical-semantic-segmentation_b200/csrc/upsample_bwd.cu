@@ -237,48 +237,25 @@ dz_band_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, 
   const int b = blockIdx.y;
   const int y_begin = blockIdx.x * band, y_end = min(H, y_begin + band);
   const long N = (long)H * W;
-  const int TP = W + XR_MAXW;  // pitch of a flush row (taps past the row end carry weight 0)
+  const int TP = W + XR_MAXW;  // pitch of a flush row (the tap window may run past the row end: zero pad)
 
   StageRing ring;
   ring.init(reinterpret_cast<uint64_t*>(smem_raw), ns, ncw);
-  float* wtab = reinterpret_cast<float*>(smem_raw + 128);              // [Wf][XR_MAXW]
-  int* wstart = reinterpret_cast<int*>(wtab + (size_t)Wf * XR_MAXW);   // [Wf]
-  int* wcnt = wstart + Wf;                                             // [Wf]
-  float* Tbuf = reinterpret_cast<float*>(smem_raw + ((128 + (size_t)Wf * (XR_MAXW + 2) * 4 + 15) & ~(size_t)15));  // [2][K][TP]
-  size_t t_end = (size_t)(reinterpret_cast<unsigned char*>(Tbuf + 2 * (size_t)K * TP) - smem_raw);
-  unsigned char* stage0 = smem_raw + ((t_end + 127) & ~(size_t)127);
-
-  // taps of the x adjoint: low-res column j receives from the contiguous run of hi-res columns that read it
-  for (int j = tid; j < Wf; j += blockDim.x) {
-    int lo, hi;
-    lerp_support(j, sx, W, lo, hi);
-    int first = -1, cnt = 0;
-    for (int x = lo; x <= hi; ++x) {
-      const float w = lerp_weight(x, sx, Wf, j);
-      if (w != 0.f || first >= 0) {
-        if (first < 0) first = x;
-        if (cnt < XR_MAXW) wtab[j * XR_MAXW + cnt] = w;
-        ++cnt;
-      }
-    }
-    for (int q = cnt; q < XR_MAXW; ++q) wtab[j * XR_MAXW + q] = 0.f;
-    wstart[j] = first < 0 ? lo : first;
-    wcnt[j] = cnt < XR_MAXW ? cnt : XR_MAXW;
-  }
-  for (int e = tid; e < 2 * K * TP; e += blockDim.x) Tbuf[e] = 0.f;  // the pad columns stay zero
+  float* Tbuf = reinterpret_cast<float*>(smem_raw + 128);  // [2][K][TP]
+  unsigned char* stage0 = smem_raw + 128 + (((size_t)2 * K * TP * 4 + 127) & ~(size_t)127);
 
   Groups<K, GSZ> gr;
-  gr.load((SRC == 1 && GROUPED) ? fa.table : nullptr);
+  gr.load((SRC == 1 && GROUPED) ? fa.table : nullptr);  // the level table is constant device data
   const bool has_act = UNIF || (!NOACT && (fa.g_uniform != nullptr || (fa.dp_pix != nullptr && fa.pix_mask != 0)));
   const int n_pp = (GROUPED && !NOACT && has_act) ? gr.n : 0;
   const int n_dpr = (!NOACT && !UNIF && has_act && fa.dp_pix != nullptr) ? n_dp : 0;  // rows of dp_pix (channels in pix_mask)
   const uint32_t rowb = (uint32_t)W * 4u;
   // stage layout: SRC 0: [K dz rows];  SRC 1: [K logit rows][K target rows][n_pp parent-probability rows][n_dpr dP rows]
   const uint32_t stage_bytes = (uint32_t)(SRC == 0 ? K : 2 * K + n_pp + n_dpr) * rowb;
-  __syncthreads();
+  __syncthreads();  // barriers initialised
 
   if (warp == ncw) {
-    // ------------------------------ producer ------------------------------
+    // ------------------------------ producer: starts fetching while the consumers set up ------------------------------
     if (lane == 0) {
       pdl_wait();
       int slot = 0;
@@ -323,7 +300,25 @@ dz_band_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, 
   auto csync = [ncons] { consumer_sync(ncons); };
   const int x0 = tid * VEC;
   const bool ok = x0 < W;  // W % VEC == 0 (launcher)
-  const int xr = ok ? x0 : 0;
+  const int xr = ok ? x0 : 0;  // lanes past the row end process (and never publish) the row start
+  // taps of the x adjoint of this thread's low-res column j = tid: the hi-res columns that read it form a contiguous
+  // run of <= XR_MAXW - 3 pixels; the weights sit in registers over a 16-byte aligned window of XR_MAXW pixels
+  float wtap[XR_MAXW];
+  int wbase = 0;
+  {
+    const int j = tid;
+    int lo = 0, hi = 0;
+    if (j < Wf) {
+      lerp_support(j, sx, W, lo, hi);
+      while (lo < hi && lerp_weight(lo, sx, Wf, j) == 0.f) ++lo;
+    }
+    wbase = lo & ~3;
+#pragma unroll
+    for (int q = 0; q < XR_MAXW; ++q) wtap[q] = (j < Wf && wbase + q < W) ? lerp_weight(wbase + q, sx, Wf, j) : 0.f;
+    // the launcher sized the window for every tap; a weight beyond it would silently be lost: fail loudly instead
+    if (j < Wf && wbase + XR_MAXW < W && lerp_weight(wbase + XR_MAXW, sx, Wf, j) != 0.f) __trap();
+  }
+  for (int e = tid; e < 2 * K * XR_MAXW; e += ncons) Tbuf[(size_t)(e / XR_MAXW) * TP + W + e % XR_MAXW] = 0.f;  // pad columns
   float A[K], Bc[K], Cc[K], gu[K];
   pdl_wait();  // coef / g_uniform are produced by the previous kernels; dz_lo was zeroed by one
   if constexpr (SRC == 1) {
@@ -343,39 +338,54 @@ dz_band_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, 
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { accA[k][v] = 0.f; accB[k][v] = 0.f; }
   int cur = make_lerp(y_begin, sy, Hf).i0;  // low-res row accA belongs to (accB: cur + 1)
+  const int last_lo = y_begin < y_end ? make_lerp(y_end - 1, sy, Hf).i1 : cur - 1;
   int tb = 0;
-
-  // finished low-res row -> shared memory -> adjoint of the x interpolation -> += dz_lo
-  auto flush = [&](const float (&acc)[K][VEC], int i_row) {
-    float* T = Tbuf + (size_t)tb * K * TP;
-    if (ok) {
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        Vec<VEC> o;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) o.v[v] = acc[k][v];
-        *reinterpret_cast<Vec<VEC>*>(T + (size_t)k * TP + x0) = o;
-      }
-    }
-    csync();
-    for (int j = tid; j < Wf; j += ncons) {
-      const float* wt = wtab + j * XR_MAXW;
-      const int ws = wstart[j], n = wcnt[j];
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const float* row = T + (size_t)k * TP + ws;
-        float a = 0.f;
-        for (int q = 0; q < n; ++q) a = fmaf(wt[q], row[q], a);
-        atomicAdd(dz_lo + (((size_t)b * K + k) * Hf + i_row) * Wf + j, a);
-      }
-    }
-    tb ^= 1;  // the next flush writes the other buffer: its barrier orders it after this one's readers
-  };
-
   int slot = 0;
   uint32_t phase = 0;
-  for (int y = y_begin; y < y_end; ++y) {
-    const Lerp ly = make_lerp(y, sy, Hf);
+  for (int y = y_begin;; ++y) {
+    // adjoint of the y interpolation lives in registers: row y feeds the low-res rows i0(y) (accA) and i0(y)+1 (accB).
+    // Rows below i0(y) are complete: each goes through shared memory once -- adjoint of the x interpolation -- and is
+    // added into dz_lo.  After the last row everything up to last_lo is flushed.
+    Lerp ly;
+    ly.i0 = last_lo + 1; ly.i1 = ly.i0; ly.l0 = 0.f; ly.l1 = 0.f;
+    if (y < y_end) ly = make_lerp(y, sy, Hf);
+    while (cur < ly.i0) {  // uniform over the CTA
+      float* T = Tbuf + (size_t)tb * K * TP;
+      if (ok) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          Vec<VEC> o;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) o.v[v] = accA[k][v];
+          *reinterpret_cast<Vec<VEC>*>(T + (size_t)k * TP + x0) = o;
+        }
+      }
+      csync();
+      if (tid < Wf) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float4* row = reinterpret_cast<const float4*>(T + (size_t)k * TP + wbase);
+          float a = 0.f;
+#pragma unroll
+          for (int q4 = 0; q4 < XR_MAXW / 4; ++q4) {
+            const float4 tv = row[q4];
+            a = fmaf(wtap[4 * q4 + 0], tv.x, a);
+            a = fmaf(wtap[4 * q4 + 1], tv.y, a);
+            a = fmaf(wtap[4 * q4 + 2], tv.z, a);
+            a = fmaf(wtap[4 * q4 + 3], tv.w, a);
+          }
+          atomicAdd(dz_lo + (((size_t)b * K + k) * Hf + cur) * Wf + tid, a);
+        }
+      }
+      tb ^= 1;  // the next flush writes the other buffer: its barrier orders it after this one's readers
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { accA[k][v] = accB[k][v]; accB[k][v] = 0.f; }
+      ++cur;
+    }
+    if (y >= y_end) break;
+
     mbar_wait(ring.full(slot), phase);
     const float* sf = reinterpret_cast<const float*>(stage0 + (size_t)slot * stage_bytes) + xr;
     float dz[K][VEC];
@@ -384,7 +394,7 @@ dz_band_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, 
       for (int k = 0; k < K; ++k) {
         const Vec<VEC> dv = *reinterpret_cast<const Vec<VEC>*>(sf + (size_t)k * W);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) dz[k][v] = ok ? dv.v[v] : 0.f;
+        for (int v = 0; v < VEC; ++v) dz[k][v] = dv.v[v];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(ring.empty(slot));
@@ -395,7 +405,7 @@ dz_band_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, 
         const Vec<VEC> zv = *reinterpret_cast<const Vec<VEC>*>(sf + (size_t)k * W);
         const Vec<VEC> tv = *reinterpret_cast<const Vec<VEC>*>(sf + (size_t)(K + k) * W);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { z[k][v] = ok ? zv.v[v] : 0.f; t[k][v] = ok ? tv.v[v] : -1.f; ex[k][v] = 0.f; }
+        for (int v = 0; v < VEC; ++v) { z[k][v] = zv.v[v]; t[k][v] = tv.v[v]; ex[k][v] = 0.f; }
       }
       int row = 2 * K;
       if constexpr (GROUPED && !NOACT) {
@@ -406,7 +416,7 @@ dz_band_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, 
           if (g < n_pp) {
             const Vec<VEC> pv = *reinterpret_cast<const Vec<VEC>*>(sf + (size_t)(row++) * W);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) ppg[g][v] = ok ? pv.v[v] : 0.f;
+            for (int v = 0; v < VEC; ++v) ppg[g][v] = pv.v[v];
           }
         }
       }
@@ -417,7 +427,7 @@ dz_band_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, 
             if ((fa.pix_mask >> k) & 1u) {
               const Vec<VEC> ev = *reinterpret_cast<const Vec<VEC>*>(sf + (size_t)(row++) * W);
 #pragma unroll
-              for (int v = 0; v < VEC; ++v) ex[k][v] = ok ? ev.v[v] : 0.f;
+              for (int v = 0; v < VEC; ++v) ex[k][v] = ev.v[v];
             }
         }
       }
@@ -492,15 +502,6 @@ dz_band_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, 
       }
     }
     if (++slot == ns) { slot = 0; phase ^= 1u; }
-    // adjoint of the y interpolation in registers
-    while (cur < ly.i0) {  // uniform over the CTA
-      flush(accA, cur);
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) { accA[k][v] = accB[k][v]; accB[k][v] = 0.f; }
-      ++cur;
-    }
     const bool two = ly.i1 > ly.i0;
 #pragma unroll
     for (int k = 0; k < K; ++k)
@@ -510,10 +511,6 @@ dz_band_kernel(const float* __restrict__ dz_hi, FusedDzArgs fa, int Hf, int Wf, 
         if (two) accB[k][v] = fmaf(ly.l1, dz[k][v], accB[k][v]);
         else accA[k][v] = fmaf(ly.l1, dz[k][v], accA[k][v]);
       }
-  }
-  if (y_begin < y_end) {
-    flush(accA, cur);
-    if (cur + 1 < Hf) flush(accB, cur + 1);
   }
 }
 
@@ -532,14 +529,17 @@ static int launch_dz_band(const float* dz_hi, const FusedDzArgs& fa, int B, int 
   static int tune_ns = -1;
   if (tune_ns < 0) { const char* e = getenv("RHSEG_TUNE_DZ_NS"); tune_ns = e ? atoi(e) : 0; }
   const int ns = tune_ns > 0 ? std::min(tune_ns, 7) : 3;
-  size_t fixed = ((128 + (size_t)Wf * (XR_MAXW + 2) * 4 + 15) & ~(size_t)15) + 2 * (size_t)K * (W + XR_MAXW) * 4;
-  fixed = (fixed + 127) & ~(size_t)127;
+  const size_t fixed = 128 + (((size_t)2 * K * (W + XR_MAXW) * 4 + 127) & ~(size_t)127);
+  if (Wf > ncons) return RHSEG_OK;  // one low-res column per consumer thread in the x adjoint
   const size_t smem = fixed + (size_t)ns * stage;
   if (smem > 200 * 1024) return RHSEG_OK;
   RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ncons + 32, smem));
   if (per_sm < 1) return RHSEG_OK;
+  static int tune_ctas = -1;
+  if (tune_ctas < 0) { const char* e = getenv("RHSEG_TUNE_DZ_CTAS"); tune_ctas = e ? atoi(e) : 0; }
+  if (tune_ctas > 0) per_sm = std::min(per_sm, tune_ctas);
   const long slots = std::max<long>(1, (long)per_sm * device_sm_count() / B);
   // >= taps per low-res row, so that at most two CTAs feed one low-res row
   const int min_band = std::max(4, (int)ceilf(2.0f / sy));
@@ -644,7 +644,10 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int hint, i
   const float sx = W > 1 ? (float)(Wf - 1) / (float)(W - 1) : 0.f;
   if constexpr (MODE != RHSEG_ACT_ZEROS || SRC == 0) {
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    bool band_ok = prezeroed && W % 4 == 0 && sx > 0.f && sy > 0.f && sy <= 1.0f && 2.0f / sx + 3.0f <= (float)XR_MAXW &&
+    // taps per low-res column (<= 2/sx + 1) plus the alignment slack of the 16-byte window must fit XR_MAXW
+    // the hi-res columns with a non-zero weight for low-res column j lie in the open interval ((j-1)/sx, (j+1)/sx):
+    // at most ceil(2/sx) of them, plus up to 3 columns of alignment slack in front
+    bool band_ok = prezeroed && W % 4 == 0 && sx > 0.f && sy > 0.f && sy <= 1.0f && ceilf(2.0f / sx) + 3.0f <= (float)XR_MAXW &&
                    !getenv("RHSEG_NO_BAND_ADJOINT");
     if (SRC == 0) band_ok = band_ok && al(dz_hi);
     else band_ok = band_ok && al(fa.logits) && al(fa.targets) && fa.t_bstride % 4 == 0 && fa.t_cstride % 4 == 0 &&
@@ -660,7 +663,9 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int hint, i
 #define RHSEG_DZB(VEC, ACTK, GS) rc = launch_dz_band<K, VEC, SRC, MODE, ACTK, GS>(dz_hi, fa, B, Hf, Wf, H, W, sy, sx, dz_lo, st, &done)
 #define RHSEG_DZB_V(ACTK, GS)                                   \
       do {                                                      \
-        if (tune_vec != 2) RHSEG_DZB(4, ACTK, GS);              \
+        if constexpr (K <= 4) {                                 \
+          if (tune_vec != 2) RHSEG_DZB(4, ACTK, GS);            \
+        }                                                       \
         if (!done && rc == RHSEG_OK) RHSEG_DZB(2, ACTK, GS);    \
       } while (0)
       if constexpr (SRC == 0) {

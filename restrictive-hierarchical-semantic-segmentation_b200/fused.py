@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import native
-from .head import alloc_weight_sums, forward_levels, level_weight_backward
+from .head import backward_buffers, forward_levels, level_weight_backward
 from .native import call, ptr, stream_of
 from .tree_tables import ClassTree
 
@@ -86,7 +86,9 @@ class _FusedStepFn(torch.autograd.Function):
                     target.data_ptr() + ch_off[L - 1] * t_cs * esz if L > 0 else None,
                     ptr(idx_maps[L - 1]) if L > 0 else None, ws.data_ptr() + offs[L][0] * 8, ptr(idx_maps[L]))
 
-        r = forward_levels(tree, out_size, tensors, evaluate, zero_words=words)
+        grad = any(ctx.needs_input_grad)  # grad mode is off inside forward(): ask autograd
+        r = forward_levels(tree, out_size, tensors, evaluate, zero_words=words, with_backward=grad)
+        ctx.bwd = r["bwd"]
         ws = r["workspace"]
         B, C, Hf, Wf, H, W = r["dims"]
         st = stream_of(r["feats"][0])
@@ -138,10 +140,10 @@ class _FusedStepFn(torch.autograd.Function):
         n_pix = H * W
         g = g_total.reshape(1)
         g = g if g.dtype == torch.float32 else g.float()
-        if ctx.upsampled:
-            sums, dz_zero = alloc_weight_sums(tree, B, C, dev, (Hf, Wf))
-        else:
-            sums, dz_zero = alloc_weight_sums(tree, B, C, dev), None
+        # accumulators zeroed by the forward's single fill; a second backward over the same graph gets fresh ones
+        bufs, ctx.bwd = ctx.bwd, None
+        if bufs is None:
+            bufs = backward_buffers(tree, B, C, dev, (Hf, Wf) if ctx.upsampled else None)
         d_feats: List[Optional[torch.Tensor]] = [None] * n
         d_hw: List[Optional[torch.Tensor]] = [None] * n
         d_hb: List[Optional[torch.Tensor]] = [None] * n
@@ -165,20 +167,19 @@ class _FusedStepFn(torch.autograd.Function):
             t_ptr = target.data_ptr() + ch_off[L] * t_cs * esz
             c_ptr = coef_all.data_ptr() + coef_offs[L] * 4
             if ctx.upsampled:
-                dz = dz_zero[L]  # zeroed together with the weight sums: the band kernel adds into it
-                tmpx = torch.empty((B, K, H, Wf), dtype=torch.float32, device=dev)  # only touched by the fallback kernels
+                dz = bufs[L]["dz"]  # zeroed together with the weight sums: the band kernel adds into it
                 call("rhseg_head_dz_lowres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, ptr(g), ptr(g),
                      ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]), ptr(g_uniform), 1.0 / n_pix, ptr(dp_pix),
-                     pix_mask, B, K, K_prev, Hf, Wf, H, W, mode, ptr(dz), ptr(dp_prev), ptr(tmpx), native.DZ_PREZEROED, st)
+                     pix_mask, B, K, K_prev, Hf, Wf, H, W, mode | tree.group_hint(L), ptr(dz), ptr(dp_prev), None,
+                     native.DZ_PREZEROED, st)
             else:
                 dz = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
                 call("rhseg_head_dz_fullres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, ptr(g), ptr(g),
                      ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]), ptr(g_uniform), 1.0 / n_pix, ptr(dp_pix),
                      pix_mask, B, K, K_prev, n_pix, mode, ptr(dz), ptr(dp_prev), st)
-            S, s, gp0 = sums[L]
             d_feats[L], d_hw[L], d_hb[L], fw_g, fb_g, g_prev = level_weight_backward(
                 tree, L, ctx.dims, feats[L], dz, eff_ws[L], head_w[L], film_w[L - 1] if L > 0 else None, gbs[L],
-                psums[L - 1] if L > 0 else None, S, s, ctx.needs_input_grad[6 + L], st, gp0)
+                psums[L - 1] if L > 0 else None, bufs[L], ctx.needs_input_grad[6 + L], st)
             if L > 0:
                 d_fw[L - 1], d_fb[L - 1] = fw_g, fb_g
             g_uniform, dp_pix, pix_mask = g_prev, dp_prev, prev_mask

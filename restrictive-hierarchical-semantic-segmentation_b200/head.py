@@ -35,7 +35,7 @@ def _side_stream(dev):
     return _SIDE_STREAMS[key]
 
 
-def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words: int = 0):
+def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words: int = 0, with_backward: bool = False):
     """Runs the per-level forward kernels.  `tensors` = feats[n] + head_w[n] + head_b[n] + film_w[n-1] +
     film_b[n-1].  Returns a dict with the inputs (contiguous fp32) and probs / logits / psums / eff_w /
     gamma_beta per level plus the shape tuple.
@@ -43,7 +43,8 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words
     (targets_ptr, t_bs, t_cs, parent_ptr, prev_idx_ptr, out_words_ptr, idx_out_ptr); the evaluation then runs
     inside the hi-res forward kernel (upsampled heads) or right after the level's forward (feature-resolution heads).
     `zero_words` extra fp64 words are zeroed by the same fill as the pool sums / low-res logits and handed to
-    `evaluate` as its third argument (the fused step's statistics workspace)."""
+    `evaluate` as its third argument (the fused step's statistics workspace).  with_backward: the same fill also
+    zeroes the accumulators of the backward pass (r["bwd"], see backward_buffers): ONE fill per training step."""
     n = tree.num_levels
     feats = [_f32c(t) for t in tensors[0:n]]
     head_w = [_f32c(t) for t in tensors[n:2 * n]]
@@ -64,10 +65,13 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words
     n_psum = sum(tree.head_channels) * B
     n_zlo = B * sum(tree.head_channels) * Hf * Wf if upsampled else 0
     n_head = (n_psum + int(zero_words) + 1) // 2 * 2  # the fp32 tail starts 16-byte aligned, as a separate allocation would
-    zero_all = torch.zeros((n_head + (n_zlo + 1) // 2,), dtype=torch.float64, device=dev)
+    n_fwd = n_head + (n_zlo + 3) // 4 * 2
+    n_bwd = backward_words(tree, B, C, (Hf, Wf) if upsampled else None) if with_backward else 0
+    zero_all = torch.zeros((n_fwd + n_bwd,), dtype=torch.float64, device=dev)
     psum_all = zero_all[:n_psum]
     workspace = zero_all[n_psum:n_psum + int(zero_words)]
-    zlo_all = zero_all[n_head:].view(torch.float32) if upsampled else None
+    zlo_all = zero_all[n_head:n_fwd].view(torch.float32) if upsampled else None
+    bwd = backward_buffers(tree, B, C, dev, (Hf, Wf) if upsampled else None, zero_all[n_fwd:]) if with_backward else None
     psum_off = 0
     used_side = False
     zlo_off = 0
@@ -80,13 +84,16 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words
         if tuple(head_w[L].shape[:2]) != (K, C):
             raise native.NativeError("head weight of level %d has shape %s, expected [%d,%d,1,1]"
                                      % (L, tuple(head_w[L].shape), K, C))
-        eff_w = torch.empty((B, K, C), dtype=torch.float32, device=dev)
-        eff_b = torch.empty((B, K), dtype=torch.float32, device=dev)
-        gb = torch.empty((B, 2 * C), dtype=torch.float32, device=dev) if L > 0 else None
-        call("rhseg_film_fold", ptr(head_w[L]), ptr(head_b[L]),
-             ptr(film_w[L - 1]) if L > 0 else None, ptr(film_b[L - 1]) if L > 0 else None,
-             ptr(psums[L - 1]) if L > 0 else None, float(n_pix), B, C, K, K_prev,
-             ptr(gb), ptr(eff_w), ptr(eff_b), st)
+        if L == 0:
+            # no FiLM in front of level 0: the kernels read the head's own [K,C] weights (flag 4: shared by all samples)
+            eff_w, eff_b, gb, shared = head_w[0], head_b[0], None, 4
+        else:
+            eff_w = torch.empty((B, K, C), dtype=torch.float32, device=dev)
+            eff_b = torch.empty((B, K), dtype=torch.float32, device=dev)
+            gb = torch.empty((B, 2 * C), dtype=torch.float32, device=dev)
+            shared = 0
+            call("rhseg_film_fold", ptr(head_w[L]), ptr(head_b[L]), ptr(film_w[L - 1]), ptr(film_b[L - 1]),
+                 ptr(psums[L - 1]), float(n_pix), B, C, K, K_prev, ptr(gb), ptr(eff_w), ptr(eff_b), st)
         z = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
         p = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
         psum = psum_all[psum_off:psum_off + B * K].view(B, K)
@@ -109,11 +116,11 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words
             call("rhseg_head_level_fwd_eval", ptr(f), ptr(eff_w), ptr(eff_b),
                  ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
                  B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L] | hint, ptr(z_lo), ptr(z), ptr(p), ptr(psum),
-                 t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, words_ptr, idx_ptr, 1 | 2, st)
+                 t_ptr, t_bs, t_cs, pt_ptr, t_bs, t_cs, pidx_ptr, words_ptr, idx_ptr, 1 | 2 | shared, st)
         else:
             call("rhseg_head_level_fwd", ptr(f), ptr(eff_w), ptr(eff_b),
                  ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]),
-                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L] | hint, ptr(z_lo), ptr(z), ptr(p), ptr(psum), 2 if upsampled else 0, st)
+                 B, C, Hf, Wf, H, W, K, K_prev, tree.act_mode[L] | hint, ptr(z_lo), ptr(z), ptr(p), ptr(psum), (2 if upsampled else 0) | shared, st)
             if ev is not None:
                 t_ptr, t_bs, t_cs, pt_ptr, pidx_ptr, words_ptr, idx_ptr = ev
                 if overlap:
@@ -133,64 +140,81 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words
     if used_side:
         torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
     return dict(feats=feats, head_w=head_w, head_b=head_b, film_w=film_w, film_b=film_b, probs=probs, logits=logits,
-                psums=psums, eff_ws=eff_ws, gbs=gbs, dims=(B, C, Hf, Wf, H, W), upsampled=upsampled, workspace=workspace)
+                psums=psums, eff_ws=eff_ws, gbs=gbs, dims=(B, C, Hf, Wf, H, W), upsampled=upsampled, workspace=workspace, bwd=bwd)
 
 
-def level_weight_backward(tree, L, dims, feats_L, dz_feat, eff_w_L, head_w_L, film_w_prev, gb_L, psum_prev, S, s,
-                          want_dfeats, st, g_prev_zeroed=None):
-    """conv backward + parameter gradients of one level given dz at feature resolution.
-    Returns (d_feats or None, d_head_w, d_head_b, d_film_w or None, d_film_b or None, g_prev or None)."""
+def level_weight_backward(tree, L, dims, feats_L, dz_feat, eff_w_L, head_w_L, film_w_prev, gb_L, psum_prev, buf, want_dfeats, st):
+    """conv backward + parameter gradients of one level given dz at feature resolution: ONE launch
+    (rhseg_head_conv_bwd_params: the last CTA to finish forms the parameter gradients from the complete sums).
+    `buf` = this level's entry of backward_buffers().  Returns (d_feats or None, d_head_w, d_head_b, d_film_w or None,
+    d_film_b or None, g_prev or None)."""
     B, C, Hf, Wf, H, W = dims
     K = tree.head_channels[L]
     K_prev = tree.head_channels[L - 1] if L > 0 else 0
     dev = feats_L.device
     d_feats = torch.empty_like(feats_L) if want_dfeats else None
-    call("rhseg_head_conv_bwd", ptr(feats_L), ptr(dz_feat), ptr(eff_w_L), B, C, K, Hf * Wf,
-         ptr(d_feats), ptr(S), ptr(s), 0, st)
     d_hw = torch.empty_like(head_w_L)
     d_hb = torch.empty((K,), dtype=torch.float32, device=dev)
     d_fw = d_fb = g_prev = None
     if L > 0:
         d_fw = torch.empty_like(film_w_prev)
         d_fb = torch.empty((2 * C,), dtype=torch.float32, device=dev)
-        # the pool-gradient accumulator: a zeroed slice of the weight-sum buffer when the caller has one
-        g_prev = g_prev_zeroed if g_prev_zeroed is not None else torch.empty((B, K_prev), dtype=torch.float64, device=dev)
-    call("rhseg_head_param_grads", ptr(S), ptr(s), ptr(head_w_L), ptr(film_w_prev) if L > 0 else None, ptr(gb_L),
-         ptr(psum_prev) if L > 0 else None, float(H * W), B, C, K, K_prev, ptr(d_hw), ptr(d_hb),
-         ptr(d_fw), ptr(d_fb), ptr(g_prev), 1 if g_prev_zeroed is not None else 0, st)
+        g_prev = buf["gp"]
+    call("rhseg_head_conv_bwd_params", ptr(feats_L), ptr(dz_feat), ptr(eff_w_L), B, C, K, Hf * Wf, ptr(d_feats),
+         ptr(buf["S"]), ptr(buf["s"]), (2 if L == 0 else 0) | 4, ptr(head_w_L), ptr(film_w_prev) if L > 0 else None, ptr(gb_L),
+         ptr(psum_prev) if L > 0 else None, float(H * W), K_prev, ptr(d_hw), ptr(d_hb), ptr(d_fw), ptr(d_fb), ptr(g_prev),
+         ptr(buf["ticket"]), st)
     return d_feats, d_hw, d_hb, d_fw, d_fb, g_prev
 
 
-def alloc_weight_sums(tree, B, C, dev, lowres_hw=None):
-    """One zero-filled fp64 buffer holding S [B,K,C], s [B,K] and the pool-gradient accumulator g_prev [B,K_prev]
-    of every level; returns per-level views (S, s, g_prev or None).
-    With lowres_hw = (Hf, Wf) the same fill also zeroes one fp32 dz_lo [B,K,Hf,Wf] per level (the band adjoint
-    kernel adds into a pre-zeroed buffer, RHSEG_DZ_PREZEROED) and (views, dz_views) is returned."""
+def _bwd_layout(tree, B, C, lowres_hw):
+    """fp64 word offsets of the backward accumulators: per level S [B,K,C] | s [B,K] | g_prev [B,K_prev] | ticket, then
+    (upsampled heads) one fp32 dz_lo [B,K,Hf,Wf] per level, each 16-byte aligned."""
     kprev = [0] + list(tree.head_channels[:-1])
-    total = sum(B * k * (C + 1) + B * kp for k, kp in zip(tree.head_channels, kprev))
-    total += total & 1  # keep the fp32 tail 16-byte aligned
-    n_lo = 0 if lowres_hw is None else lowres_hw[0] * lowres_hw[1]
-    lo_words = [(B * k * n_lo + 3) // 4 * 2 for k in tree.head_channels]  # fp64 words per level, 16-byte multiples
-    buf = torch.zeros((total + sum(lo_words),), dtype=torch.float64, device=dev)
-    views, off = [], 0
+    off, levels = 0, []
     for k, kp in zip(tree.head_channels, kprev):
-        gp = buf[off + B * k * (C + 1):off + B * k * (C + 1) + B * kp].view(B, kp) if kp else None
-        views.append((buf[off:off + B * k * C].view(B, k, C), buf[off + B * k * C:off + B * k * (C + 1)].view(B, k), gp))
-        off += B * k * (C + 1) + B * kp
-    if lowres_hw is None:
-        return views
-    dz_views, off = [], total
-    for k, w in zip(tree.head_channels, lo_words):
-        dz_views.append(buf[off:off + w].view(torch.float32)[:B * k * n_lo].view(B, k, lowres_hw[0], lowres_hw[1]))
-        off += w
-    return views, dz_views
+        lv = dict(S=off, s=off + B * k * C, gp=off + B * k * (C + 1), ticket=off + B * k * (C + 1) + B * kp, k=k, kp=kp)
+        off = lv["ticket"] + 1
+        levels.append(lv)
+    off += off & 1
+    n_lo = 0 if lowres_hw is None else lowres_hw[0] * lowres_hw[1]
+    for lv in levels:
+        lv["dz"] = off
+        off += (B * lv["k"] * n_lo + 3) // 4 * 2
+    return levels, off
+
+
+def backward_words(tree, B, C, lowres_hw=None):
+    return _bwd_layout(tree, B, C, lowres_hw)[1]
+
+
+def backward_buffers(tree, B, C, dev, lowres_hw=None, zeroed=None):
+    """Zero-filled accumulators of the backward pass as per-level dicts of views: S, s, gp (pool-gradient accumulator,
+    None at level 0), ticket (the conv kernel's last-CTA counter) and, with lowres_hw = (Hf, Wf), dz (the fp32 dz_lo the
+    band adjoint adds into, RHSEG_DZ_PREZEROED).  `zeroed`: a zero fp64 tensor of backward_words() elements to carve the
+    views from (the forward's single fill); otherwise one torch.zeros is made here."""
+    levels, total = _bwd_layout(tree, B, C, lowres_hw)
+    buf = zeroed if zeroed is not None else torch.zeros((total,), dtype=torch.float64, device=dev)
+    out = []
+    for lv in levels:
+        k, kp = lv["k"], lv["kp"]
+        d = dict(S=buf[lv["S"]:lv["S"] + B * k * C].view(B, k, C), s=buf[lv["s"]:lv["s"] + B * k].view(B, k),
+                 gp=buf[lv["gp"]:lv["gp"] + B * kp].view(B, kp) if kp else None,
+                 ticket=buf[lv["ticket"]:lv["ticket"] + 1].view(torch.int32), dz=None)
+        if lowres_hw is not None:
+            n = B * k * lowres_hw[0] * lowres_hw[1]
+            d["dz"] = buf[lv["dz"]:lv["dz"] + (n + 3) // 4 * 2].view(torch.float32)[:n].view(B, k, lowres_hw[0], lowres_hw[1])
+        out.append(d)
+    return out
 
 
 class _HierHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tree: ClassTree, out_size: Optional[Tuple[int, int]], *tensors):
         n = tree.num_levels
-        r = forward_levels(tree, out_size, tensors)
+        grad = any(ctx.needs_input_grad)  # grad mode is off inside forward(): ask autograd
+        r = forward_levels(tree, out_size, tensors, with_backward=grad)
+        ctx.bwd = r["bwd"]
         feats, head_w, film_w = r["feats"], r["head_w"], r["film_w"]
         probs, logits, psums, eff_ws, gbs = r["probs"], r["logits"], r["psums"], r["eff_ws"], r["gbs"]
         ctx.tree, ctx.dims, ctx.upsampled = tree, r["dims"], r["upsampled"]
@@ -221,10 +245,10 @@ class _HierHeadFn(torch.autograd.Function):
         d_fw: List[Optional[torch.Tensor]] = [None] * (n - 1)
         d_fb: List[Optional[torch.Tensor]] = [None] * (n - 1)
 
-        if ctx.upsampled:
-            sums, dz_zero = alloc_weight_sums(tree, B, C, dev, (Hf, Wf))
-        else:
-            sums, dz_zero = alloc_weight_sums(tree, B, C, dev), None
+        # accumulators zeroed by the forward's fill; a second backward over the same graph gets fresh ones
+        bufs, ctx.bwd = ctx.bwd, None
+        if bufs is None:
+            bufs = backward_buffers(tree, B, C, dev, (Hf, Wf) if ctx.upsampled else None)
         g_uniform = None   # [B,K_L] fp64: dLoss/d(sum_n P_L) * n_pix, from level L+1's FiLM
         dp_pix = None      # [B,K_L,H,W]: per-pixel dLoss/dP_L (composition of level L+1 and/or user grads)
         pix_mask = 0
@@ -257,14 +281,12 @@ class _HierHeadFn(torch.autograd.Function):
             if dz is None:
                 continue  # nothing reaches this level's logits: no gradient for its features / parameters
             if ctx.upsampled:
-                dz_lo = dz_zero[L]  # zeroed together with the weight sums
-                tmpx = torch.empty((B, K, H, Wf), dtype=torch.float32, device=dev)
-                call("rhseg_upsample_adjoint", ptr(dz), B, K, Hf, Wf, H, W, ptr(dz_lo), ptr(tmpx), native.DZ_PREZEROED, st)
+                dz_lo = bufs[L]["dz"]  # zeroed together with the weight sums: the band adjoint adds into it
+                call("rhseg_upsample_adjoint", ptr(dz), B, K, Hf, Wf, H, W, ptr(dz_lo), None, native.DZ_PREZEROED, st)
                 dz = dz_lo
-            S, s, gp0 = sums[L]
             d_feats[L], d_hw[L], d_hb[L], fw_g, fb_g, g_prev = level_weight_backward(
                 tree, L, ctx.dims, feats[L], dz, eff_ws[L], head_w[L], film_w[L - 1] if L > 0 else None, gbs[L],
-                psums[L - 1] if L > 0 else None, S, s, ctx.needs_input_grad[2 + L], st, gp0)
+                psums[L - 1] if L > 0 else None, bufs[L], ctx.needs_input_grad[2 + L], st)
             if L > 0:
                 d_fw[L - 1], d_fb[L - 1] = fw_g, fb_g
             g_uniform = g_prev

@@ -43,6 +43,7 @@ SIGNATURES = {
     "rhseg_xchg_status": [_P, _P],
     "rhseg_xchg_destroy": [_P],
     "rhseg_head_conv_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P],
+    "rhseg_head_conv_bwd_params": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _D, _I, _P, _P, _P, _P, _P, _P, _P],
     "rhseg_head_param_grads": [_P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "rhseg_loss_stats": [_P, _P, _L, _L, _I, _I, _I, _I, _P, _P],
     "rhseg_loss_finalize": [_P, _P, _I, _I, _D, _P, _P, _P],

@@ -1,0 +1,136 @@
+"""The reference's OWN glue on top of the drop-in modules, on the GPU.
+
+train.py (train.train_epoch :161-279, train.get_loss :111-152, train.get_metrics :38-81) is imported UNCHANGED from
+the staged reference (oracle/_ref, or /root/reference in the build container) with the package directory ahead of it
+on sys.path, so its `from Models import models`, `from Metrics import losses, performance_metrics` resolve to the
+sm_100a drop-in modules.  Expected values come from tests/golden/glue_*.npz: the same train.train_epoch run with the
+reference's own Models / Metrics.losses on CPU (tests/golden/make_glue_golden.py)."""
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, HIER_CASES, Fixture, close
+from oracle import hier_oracle as O
+from oracle import ref_loader
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_loader.available(), reason="reference not staged (tools/stage_reference.py)")]
+DEV = "cuda"
+
+
+def _glue_module():
+    spec = importlib.util.spec_from_file_location("make_glue_golden", os.path.join(GOLDEN, "make_glue_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture()
+def dropin_train():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    train = ref_loader.load_train_with_dropin()
+    yield train
+    ref_loader.restore_package_imports()
+
+
+@pytest.mark.parametrize("name", ["glue_unet_tl", "glue_unet_tl_curriculum"])
+def test_reference_train_epoch_runs_on_the_dropin_modules(dropin_train, name):
+    glue = _glue_module()
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    train = dropin_train
+    models, losses, pm = sys.modules["Models.models"], sys.modules["Metrics.losses"], sys.modules["Metrics.performance_metrics"]
+    assert "restrictive-hierarchical-semantic-segmentation_b200" in models.__file__
+    model = models.UNet(size=48, n_channels=3, hierarchy=meta["tree"], model_type=1)
+    glue.attach_tiny_donor(model)
+    init = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("init.")}
+    missing, unexpected = model.load_state_dict(init, strict=False)
+    assert not unexpected and all(not m.startswith(("tiny_donor", "heads", "films")) for m in missing)
+    model.to(DEV)
+    batches = [(torch.from_numpy(z["data%d" % i]), torch.from_numpy(z["target%d" % i]).float()) for i in range(meta["n_batches"])]
+    metric_objs = [pm.Accuracy(), pm.Jaccardindex(), pm.DiceScore(), pm.Precision(), pm.Recall()]
+    out = glue.run_epoch(train, model, losses, metric_objs, batches, meta["tree"], torch.device(DEV), meta["pretrain"],
+                         meta["epoch_num"], meta["lr"])
+    got = glue.pack_result(out)
+    assert abs(got["loss"] - z["loss"]) <= 2e-5 * abs(z["loss"]), (got["loss"], z["loss"])
+    np.testing.assert_allclose(got["level_loss"], z["level_loss"], rtol=2e-5, atol=1e-7)
+    # metrics are ratios of pixel counts: identical unless a near-tie pixel flips between the CPU and GPU donors
+    for key in ("accuracy", "iou", "dice", "precision", "recall"):
+        assert abs(got[key] - z[key]) <= 2e-4, (key, got[key], z[key])
+    np.testing.assert_allclose(got["class_metrics"], z["class_metrics"], atol=5e-4)
+    # parameters after the optimiser steps: head, FiLM and donor weights received the reference's gradients
+    for k in z.files:
+        if k.startswith("final."):
+            close(model.state_dict()[k[6:]], torch.from_numpy(z[k]), rtol=2e-5, what=k)
+    moved = max(float((torch.from_numpy(z["final." + k]) - v).abs().max()) for k, v in init.items())
+    assert moved > 1e-4  # the epoch did train
+
+
+@pytest.mark.parametrize("name", HIER_CASES)
+def test_reference_get_loss_and_get_metrics_on_dropin_outputs(dropin_train, name):
+    """train.get_loss (:111-152) / train.get_metrics (:38-81) called the way train_epoch calls them, on the outputs of the
+    drop-in head for the reference-generated fixtures: loss and gradients against the reference's recorded values, the
+    metrics against the restated torchmetrics slice."""
+    import rhseg_b200
+    import types
+    train = dropin_train
+    losses, pm = sys.modules["Metrics.losses"], sys.modules["Metrics.performance_metrics"]
+    fx = Fixture(name)
+    tree = rhseg_b200.ClassTree(fx.tree)
+    mk = lambda ts: [t.to(DEV).requires_grad_(True) for t in ts]
+    feats = mk(fx.per_level("feats"))
+    hw, hb = mk(fx.per_level("head_w")), mk(fx.per_level("head_b"))
+    fw, fb = mk(fx.per_level("film_w", n=fx.nL - 1)), mk(fx.per_level("film_b", n=fx.nL - 1))
+    probs, logits = rhseg_b200.hier_head_forward(tree, feats, hw, hb, fw, fb, fx.out_size)
+    target = torch.cat(fx.per_level("target"), dim=1).to(DEV)
+    targets, s = [], 0
+    for k in tree.head_channels:  # train.py:185-193
+        targets.append(target[:, s:s + k])
+        s += k
+    # train.py:206-231 (the reference's own lines, restated only because they live inside train_epoch's loop body)
+    output_class = [torch.nn.functional.one_hot(torch.argmax(torch.softmax(z, dim=1), dim=1), num_classes=z.shape[1])
+                    .permute(0, 3, 1, 2).float() for z in logits]
+    eval_targets = list(targets)
+    for i in range(len(targets)):
+        output_class[i] = torch.where(targets[i] == -1, 0, output_class[i])
+        eval_targets[i] = torch.where(targets[i] == -1, 0, targets[i])
+    nK = sum(tree.head_channels)
+    clss = [{k: [] for k in ("accuracy", "iou", "dice", "precision", "recall")} for _ in range(nK)]
+    acc, iou, dice, prec, rec = [], [], [], [], []
+    args = types.SimpleNamespace()
+    clss, acc, iou, dice, prec, rec, _ = train.get_metrics(output_class, eval_targets, acc, iou, dice, prec, rec, pm.Accuracy(),
+                                                           pm.Jaccardindex(), pm.DiceScore(), pm.Precision(), pm.Recall(), DEV, clss, args)
+    want = {k: [] for k in ("accuracy", "iou", "dice", "precision", "recall")}
+    for L in range(fx.nL):
+        onehot = fx.t(f"onehot{L}")
+        et = torch.where(fx.t(f"target{L}") == -1, 0, fx.t(f"target{L}"))
+        r = O.ratios_from_confusion(O.level_confusion(onehot, et, onehot.shape[1], L != 0))
+        for k in want:
+            want[k] += (r[k][1:] if L else r[k]).tolist()
+    for c in range(nK):
+        for k in want:
+            assert clss[c][k][0] == pytest.approx(want[k][c], abs=1e-7), (name, c, k)
+    assert dice[0] == pytest.approx(float(np.mean(want["dice"])), abs=1e-6)
+
+    class M:  # what get_loss reads off the model (train.py:146)
+        levels, parent_of = tree.levels, tree.parent_of
+
+    loss_fns = [[losses.CrossEntropyLoss(), losses.SoftDiceLoss()] for _ in range(fx.nL)]
+    level_loss = []
+    loss, _, level_loss = train.get_loss(logits, targets, loss_fns, level_loss, fx.level_weights, 0.0, [], cur_epoch=0,
+                                         pretrain_epoch=None, probs_per_level=output_class, model=M)
+    ref_total = fx.f("total_loss")
+    assert abs(loss.item() - ref_total) <= 1e-5 * abs(ref_total), (loss.item(), ref_total)
+    loss.backward()
+    for L in range(fx.nL):
+        close(feats[L].grad, fx.t(f"dfeats{L}"), what=f"{name} dfeats{L}")
+        close(hw[L].grad, fx.t(f"dhead_w{L}"), what=f"{name} dhead_w{L}")
+        close(hb[L].grad, fx.t(f"dhead_b{L}"), what=f"{name} dhead_b{L}")
+    for i in range(fx.nL - 1):
+        close(fw[i].grad, fx.t(f"dfilm_w{i}"), what=f"{name} dfilm_w{i}")
+        close(fb[i].grad, fx.t(f"dfilm_b{i}"), what=f"{name} dfilm_b{i}")

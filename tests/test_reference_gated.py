@@ -9,8 +9,12 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.environ.get("RHSEG_REFERENCE_ROOT", "/root/reference")
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+
+# /root/reference in the build container, the staged byte copies (oracle/_ref, tools/stage_reference.py) elsewhere
+REF = ref_loader.reference_root() or "/root/reference"
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 
@@ -109,3 +113,30 @@ def test_oracle_stitching_matches_reference_predicteval():
         want = pe.combine_levels([flat], par, tree, names, parent_order)
         got = O.stitch_flat_to_levels(flat, tree)
         assert len(want) == len(got) and all(torch.equal(a, b) for a, b in zip(want, got))
+
+
+def test_oracle_process_classes_pinned_to_reference():
+    """ProcessClasses (Metrics/performance_metrics.py:27-47) is torch-only: the reference's own class, imported with the
+    torchmetrics import stubbed, pins the oracle's restatement (and through it the CUDA confusion kernels) on the three
+    kinds of input that reach it: masked one-hots, composed probabilities, ties / all-zero pixels."""
+    ref_shim, _ = _ref()
+    rpm = ref_loader.load_reference_module("Metrics.performance_metrics")
+    from oracle import hier_oracle as O
+    theirs = rpm.ProcessClasses()
+    g = torch.Generator().manual_seed(9)
+    for K in (1, 2, 3, 4, 7):
+        B, H, W = 2, 13, 17
+        lab = torch.randint(0, K, (B, H, W), generator=g)
+        onehot = torch.nn.functional.one_hot(lab, K).permute(0, 3, 1, 2).float()
+        ignore = torch.rand(B, 1, H, W, generator=g) < 0.3
+        masked = torch.where(ignore, torch.zeros_like(onehot), onehot)            # train.py:230
+        probs = torch.rand(B, K, H, W, generator=g)
+        probs[:, :, :2] = 0.0                                                     # nothing positive
+        probs[:, :, 2:4] = probs[:, :1, 2:4]                                      # exact ties
+        tgt = torch.nn.functional.one_hot(torch.randint(0, K, (B, H, W), generator=g), K).permute(0, 3, 1, 2).float()
+        tgt = torch.where(torch.rand(B, 1, H, W, generator=g) < 0.4, torch.zeros_like(tgt), tgt)
+        for p in (masked, probs):
+            for child in (False, True):
+                a, b = theirs(p, tgt, child)
+                c, d = O.process_classes(p, tgt, child)
+                assert torch.equal(a, c.to(a.dtype)) and torch.equal(b, d.to(b.dtype)), (K, child)
