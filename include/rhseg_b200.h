@@ -289,7 +289,19 @@ int rhseg_head_dz_fullres_fused(const float* logits, const float* targets, long 
  * counts as fp64.                                                                           */
 int rhseg_step_finalize(const void* eval_words, const float* weights_all, int B, int n_levels,
                         const int32_t* K_per_level, const int32_t* groups_per_level, double smooth,
-                        long n_pix, float* out, float* coef_all, double* summary, void* stream);
+                        long n_pix, unsigned level_mask, float* out, float* coef_all, double* summary, void* stream);
+/* level_mask: bit L set = level L's CE + Dice enter the total (train.get_loss's level-pretrain curriculum,
+ * train.py:125-134, skips levels L > cur_epoch // pretrain_epoch; their per-level values, metrics and the consistency
+ * term are still reported, as the reference does).  All ones = every level.                                      */
+
+/* Data-parallel gradient factors (reference semantics Metrics/losses.py:64-66, :117-119: CE is a mean
+ * over all samples of the GLOBAL batch, Dice over the GLOBAL number of non-NaN samples).  local / global = this rank's
+ * rhseg_step_finalize summary and its SUM over ranks; g = the upstream gradient (device scalar, NULL -> 1).
+ *   out[2L]   = g * world * B_local / B_global             (-> g_ce   of rhseg_head_dz_*_fused at level L)
+ *   out[2L+1] = g * world * n_valid_local[L] / n_valid_global[L]   (-> g_dice; 0 when no sample is valid anywhere)
+ * so that the mean over ranks of the per-rank gradients equals the single-process gradient on the concatenated batch. */
+int rhseg_dp_grad_scales(const double* local_summary, const double* global_summary, int n_levels, int world,
+                         const float* g, float* out, void* stream);
 
 /* Fused per-level TRAINING evaluation (train.py:206-239 for one level in one pass): loss
  * statistics + train-path prediction + confusion matrix of the masked one-hot prediction +
@@ -343,7 +355,12 @@ int rhseg_unpack_f32(const double* in, double scale, void* const* dsts, const lo
  *                       srcs_r[k][i]  (srcs / counts as in rhseg_pack_f64; out may alias summary;
  *                       n_sum + sum counts <= capacity).  Every rank calls it with the same sizes, in
  *                       the same order.
- *   rhseg_xchg_status : 0, or 1 when a wait for a peer timed out (~2 s; the result is then invalid).
+ *   rhseg_xchg_status : 0, or 1 (sticky) when a wait for a peer timed out.  A timeout is a hard failure: that exchange
+ *                       and every later one of the context writes NaN into the WHOLE result, so the loss and the
+ *                       gradients poison visibly instead of the replicas diverging; the host raises at its next sync
+ *                       point (dist.PeerExchange.check).  Synchronises the device.
+ *   rhseg_xchg_set_timeout_ms: wait limit per exchange, default 30 s (RHSEG_XCHG_TIMEOUT_MS), 0 = wait for ever like an
+ *                       NCCL all-reduce.  Applies to launches (and graph captures) made after the call.
  * World size <= 16.                                                                               */
 #define RHSEG_XCHG_HANDLE_BYTES 64
 int rhseg_xchg_create(long capacity, int world, void** ctx_out, unsigned char* handle_out);
@@ -351,6 +368,7 @@ int rhseg_xchg_connect(void* ctx, int rank, const unsigned char* handles);
 int rhseg_xchg_all_reduce(void* ctx, const double* summary, long n_sum, const void* const* srcs,
                           const long* counts, int n, double* out, void* stream);
 int rhseg_xchg_status(void* ctx, int* status_out);
+int rhseg_xchg_set_timeout_ms(void* ctx, long ms);
 int rhseg_xchg_destroy(void* ctx);
 
 #ifdef __cplusplus

@@ -106,12 +106,13 @@ extern "C" int rhseg_unpack_f32(const double* in, double scale, void* const* dst
 namespace rhseg {
 
 constexpr int XCHG_MAX_WORLD = 16, XCHG_MAX_CTA = 32, XCHG_THREADS = 256, XCHG_ELEMS = 2;
-constexpr long XCHG_SPIN_LIMIT = 20L * 1000 * 1000;  // polls of ~100 ns: a peer that never shows up ends the wait after ~2 s
+constexpr unsigned long long XCHG_DEFAULT_TIMEOUT_NS = 30ull * 1000 * 1000 * 1000;  // RHSEG_XCHG_TIMEOUT_MS / rhseg_xchg_set_timeout_ms
 
 struct XchgDev {
   uint4* recv[XCHG_MAX_WORLD];  // peer r's receive area [2][world][cap]
   uint32_t* epoch;              // local [MAX_CTA]
-  uint32_t* status;             // local: 0 ok, 1 = a wait timed out
+  uint32_t* status;             // local, sticky: 0 ok, 1 = a wait for a peer timed out (every result from then on is NaN)
+  unsigned long long timeout_ns;  // 0 = wait for ever (what an NCCL all-reduce does)
   long cap;
   int rank, world;
 };
@@ -123,7 +124,14 @@ struct XchgCtx {
   size_t recv_bytes;
   int world;
   bool connected;
+  unsigned char own_handle[RHSEG_XCHG_HANDLE_BYTES];
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void st_record(uint4* p, uint32_t lo, uint32_t hi, uint32_t ep) {
   asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(ep), "r"(hi), "r"(ep) : "memory");
@@ -139,6 +147,10 @@ xchg_all_reduce_kernel(XchgDev d, const double* summary, long n_sum, XchgParts p
   pdl_wait();
   const int cta = blockIdx.x, tid = threadIdx.x;
   const uint32_t ep = d.epoch[cta] + 1u;  // every thread reads it before anybody of this CTA can have written it
+  // A timeout is a hard failure: once a peer was missed the epochs of the ranks no longer agree, so this and every
+  // later exchange of the context poisons its whole result with NaN (loss and gradients turn NaN visibly instead
+  // of the replicas diverging silently); the host reads the sticky status at its next sync point (PeerExchange.check).
+  bool failed = *reinterpret_cast<volatile uint32_t*>(d.status) != 0u;
   __syncthreads();
   const size_t slot_base = (size_t)(ep & 1u) * d.world * (size_t)d.cap;
   const long stride = (long)gridDim.x * XCHG_THREADS;
@@ -173,10 +185,17 @@ xchg_all_reduce_kernel(XchgDev d, const double* summary, long n_sum, XchgParts p
           if (r != d.rank) {
             const uint4* src = d.recv[d.rank] + slot_base + (size_t)r * d.cap + i;
             uint4 rec = ld_record(src);
-            long spins = 0;
-            while (rec.y != ep || rec.w != ep) {
-              if (++spins > XCHG_SPIN_LIMIT) { *d.status = 1u; break; }
-              rec = ld_record(src);
+            if (!failed && (rec.y != ep || rec.w != ep)) {
+              const unsigned long long t0 = d.timeout_ns ? global_ns() : 0ull;
+              unsigned spins = 0;
+              do {
+                if (d.timeout_ns && (++spins & 1023u) == 0u && global_ns() - t0 > d.timeout_ns) {
+                  *reinterpret_cast<volatile uint32_t*>(d.status) = 1u;
+                  failed = true;
+                  break;
+                }
+                rec = ld_record(src);
+              } while (rec.y != ep || rec.w != ep);
             }
             val = __longlong_as_double((long long)(((unsigned long long)rec.z << 32) | rec.x));
           }
@@ -186,7 +205,10 @@ xchg_all_reduce_kernel(XchgDev d, const double* summary, long n_sum, XchgParts p
       }
     }
   }
-  __syncthreads();
+  if (__syncthreads_or(failed ? 1 : 0)) {  // poison everything this CTA wrote (other CTAs see the sticky status themselves)
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (long i = (long)cta * XCHG_THREADS + tid; i < total; i += stride) out[i] = nan;
+  }
   // all per-CTA counters advance together (CTA 0 also bumps those of the CTAs this launch did not use), so the
   // epoch is the number of exchanges done, whatever grid each of them ran with
   if (tid == 0) d.epoch[cta] = ep;
@@ -214,7 +236,10 @@ extern "C" int rhseg_xchg_create(long capacity, int world, void** ctx_out, unsig
   }
   static_assert(sizeof(cudaIpcMemHandle_t) == RHSEG_XCHG_HANDLE_BYTES, "IPC handle size");
   memcpy(handle_out, &h, sizeof(h));
+  memcpy(c->own_handle, &h, sizeof(h));
   c->dev.cap = capacity;
+  c->dev.timeout_ns = XCHG_DEFAULT_TIMEOUT_NS;
+  if (const char* e = getenv("RHSEG_XCHG_TIMEOUT_MS")) c->dev.timeout_ns = (unsigned long long)std::max(0L, atol(e)) * 1000000ull;
   c->connected = false;
   *ctx_out = c;
   return RHSEG_OK;
@@ -226,7 +251,9 @@ extern "C" int rhseg_xchg_connect(void* ctx, int rank, const unsigned char* hand
   if (c->connected) return RHSEG_ERR_ARG;
   for (int r = 0; r < c->world; ++r) {
     void* base = c->local_base;
-    if (r != rank) {
+    // a peer entry that carries this rank's own handle maps to the local area (single-process tests of the timeout path:
+    // nobody ever writes that "peer's" records)
+    if (r != rank && memcmp(handles + (size_t)r * RHSEG_XCHG_HANDLE_BYTES, c->own_handle, RHSEG_XCHG_HANDLE_BYTES) != 0) {
       cudaIpcMemHandle_t h;
       memcpy(&h, handles + (size_t)r * RHSEG_XCHG_HANDLE_BYTES, sizeof(h));
       RHSEG_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
@@ -272,12 +299,19 @@ extern "C" int rhseg_xchg_status(void* ctx, int* status_out) {
   return RHSEG_OK;
 }
 
+extern "C" int rhseg_xchg_set_timeout_ms(void* ctx, long ms) {
+  XchgCtx* c = static_cast<XchgCtx*>(ctx);
+  if (!c || ms < 0) return RHSEG_ERR_ARG;
+  c->dev.timeout_ns = (unsigned long long)ms * 1000000ull;  // read by the launches that follow (a captured graph keeps its own)
+  return RHSEG_OK;
+}
+
 extern "C" int rhseg_xchg_destroy(void* ctx) {
   XchgCtx* c = static_cast<XchgCtx*>(ctx);
   if (!c) return RHSEG_ERR_ARG;
   if (c->connected)
     for (int r = 0; r < c->world; ++r)
-      if (r != c->dev.rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+      if (r != c->dev.rank && c->peer_base[r] && c->peer_base[r] != c->local_base) cudaIpcCloseMemHandle(c->peer_base[r]);
   if (c->local_base) cudaFree(c->local_base);
   delete c;
   return RHSEG_OK;

@@ -221,7 +221,7 @@ __device__ __forceinline__ SampleLoss sample_loss(const double* __restrict__ st,
 // All levels in parallel: thread <-> (level, sample); shared-memory fp64 atomics per level.
 __global__ void __launch_bounds__(256)
 step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ weights, StepLevels lv, int B,
-                     double smooth, double inv_bn, float* __restrict__ out, float* __restrict__ coef,
+                     double smooth, double inv_bn, unsigned level_mask, float* __restrict__ out, float* __restrict__ coef,
                      double* __restrict__ summary) {
   pdl_wait();
   __shared__ double acc[RHSEG_MAX_LEVELS][4];  // ce_sum, dice_sum, n_dice, n_ce
@@ -303,7 +303,7 @@ step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ we
       const float ce = (float)fast_div(acc[L][0], (double)B);
       const float dice = acc[L][2] > 0.0 ? (float)fast_div(acc[L][1], acc[L][2]) : 0.f;
       out[2 + 4 * L] = ce; out[3 + 4 * L] = dice; out[4 + 4 * L] = (float)acc[L][2]; out[5 + 4 * L] = (float)acc[L][3];
-      total += ce + dice;  // CE_L + Dice_L (0 when no sample is valid)
+      if ((level_mask >> L) & 1u) total += ce + dice;  // CE_L + Dice_L (0 when no sample is valid); curriculum: train.py:125-134
     }
     const float consf = cons_count > 0 ? (float)fast_div(cons_total, (double)cons_count) : 0.f;
     out[0] = total + consf;
@@ -526,7 +526,7 @@ extern "C" int rhseg_consistency_sums(const float* cur, const float* prev, const
 
 extern "C" int rhseg_step_finalize(const void* eval_words, const float* weights_all, int B, int n_levels,
                                    const int32_t* K_per_level, const int32_t* groups_per_level, double smooth,
-                                   long n_pix, float* out, float* coef_all, double* summary, void* stream) {
+                                   long n_pix, unsigned level_mask, float* out, float* coef_all, double* summary, void* stream) {
   if (!eval_words || !weights_all || !K_per_level || !groups_per_level || !out || !coef_all) return RHSEG_ERR_ARG;
   if (B <= 0 || n_levels < 1 || n_levels > RHSEG_MAX_LEVELS || n_pix <= 0) return RHSEG_ERR_ARG;
   StepLevels lv{};
@@ -538,7 +538,35 @@ extern "C" int rhseg_step_finalize(const void* eval_words, const float* weights_
     lv.child[L] = L == 0 ? 0 : 1;
   }
   launch_pdl(step_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const double*>(eval_words), weights_all, lv, B,
-                                                            smooth, 1.0 / ((double)B * (double)n_pix), out, coef_all, summary);
+                                                            smooth, 1.0 / ((double)B * (double)n_pix), level_mask, out, coef_all, summary);
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
+namespace rhseg {
+// Data-parallel gradient factors: the single-process reference averages CE over ALL samples of the
+// global batch and Dice over the GLOBAL count of non-NaN samples (Metrics/losses.py:64-66, :117-119); a rank that
+// back-propagates its local means and lets DDP average over ranks gets exactly that when its CE gradient is scaled
+// by world*B_local/B_global and its Dice gradient by world*n_valid_local/n_valid_global.
+__global__ void dp_grad_scales_kernel(const double* __restrict__ local, const double* __restrict__ global, int n_levels,
+                                      double world, const float* __restrict__ g, float* __restrict__ out) {
+  pdl_wait();
+  const int L = threadIdx.x;
+  if (L >= n_levels) return;
+  const double up = g ? (double)g[0] : 1.0;
+  const double bl = local[0], bg = global[0];
+  const double nl = local[4 + 4 * L], ng = global[4 + 4 * L];
+  out[2 * L + 0] = (float)(bg > 0.0 ? up * world * bl / bg : 0.0);
+  out[2 * L + 1] = (float)(ng > 0.0 ? up * world * nl / ng : 0.0);
+}
+}  // namespace rhseg
+
+extern "C" int rhseg_dp_grad_scales(const double* local_summary, const double* global_summary, int n_levels, int world,
+                                    const float* g, float* out, void* stream) {
+  if (!local_summary || !global_summary || !out || world < 1) return RHSEG_ERR_ARG;
+  if (n_levels < 1 || n_levels > RHSEG_MAX_LEVELS) return RHSEG_ERR_ARG;
+  launch_pdl(rhseg::dp_grad_scales_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, local_summary, global_summary, n_levels,
+             (double)world, g, out);
   RHSEG_LAUNCH_CHECK();
   return RHSEG_OK;
 }

@@ -177,12 +177,27 @@ class PeerExchange:
         return out[:need]
 
     def status(self) -> int:
-        """0, or 1 when a wait for a peer timed out (synchronises the device)."""
+        """0, or 1 (sticky) when a wait for a peer timed out (synchronises the device)."""
         import ctypes
         from . import native
         s = ctypes.c_int(0)
         native.check(native.lib().rhseg_xchg_status(self._ctx, ctypes.byref(s)), "rhseg_xchg_status")
         return int(s.value)
+
+    def check(self) -> None:
+        """Raises when an exchange timed out.  A timeout is a hard failure: the kernel poisons that result and every later
+        one with NaN (so loss and gradients turn NaN rather than the replicas diverging silently); call this at a host
+        sync point the training loop already has (where it reads the loss, or around the optimiser step)."""
+        from . import native
+        if self.status() != 0:
+            raise native.NativeError("peer-memory exchange timed out waiting for a rank (rank %d of %d): results since then "
+                                     "are NaN; the job must stop" % (self.rank, self.world))
+
+    def set_timeout_ms(self, ms: int) -> None:
+        """Wait limit per exchange (default 30 s, RHSEG_XCHG_TIMEOUT_MS); 0 waits for ever, like an NCCL all-reduce.
+        Applies to exchanges launched (or captured into a graph) afterwards."""
+        from . import native
+        native.check(native.lib().rhseg_xchg_set_timeout_ms(self._ctx, int(ms)), "rhseg_xchg_set_timeout_ms")
 
     def close(self):
         if getattr(self, "_ctx", None):

@@ -30,11 +30,12 @@ _I32 = ctypes.c_int32
 class StepOutput:
     """Everything one training step reports, still on the device (no host sync)."""
     __slots__ = ("loss", "scalars", "level_ce", "level_dice", "consistency", "confusion", "ratios", "probs", "logits",
-                 "summary", "exchange")
+                 "summary", "exchange", "global_summary")
 
-    def __init__(self, loss, scalars, confusion, ratios, probs, logits, n, summary=None, exchange=None):
+    def __init__(self, loss, scalars, confusion, ratios, probs, logits, n, summary=None, exchange=None, global_summary=None):
         self.summary = summary                 # fp64 additive per-rank summary for dist.all_reduce_summary
         self.exchange = exchange               # summary + `exchange_tail` free fp64 slots behind it (dist.pack_exchange)
+        self.global_summary = global_summary   # data-parallel steps: SUM over ranks of `summary` (dist.unpack_global reads it)
         self.loss = loss                       # 0-dim, differentiable
         self.scalars = scalars                 # [2 + 4*n] fp32: total, consistency, then (ce, dice, n_dice, n_ce) per level
         self.consistency = scalars[1]
@@ -57,8 +58,9 @@ def _eval_layout(tree: ClassTree, B: int):
 
 class _FusedStepFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tree: ClassTree, out_size, weights_all, smooth, xchg_tail, target, *tensors):
+    def forward(ctx, tree: ClassTree, out_size, weights_all, smooth, xchg_tail, level_cap, dp, target, *tensors):
         n = tree.num_levels
+        n_active = n if level_cap is None else max(1, min(n, int(level_cap) + 1))  # train.py:121-126
         native.require_cuda(target)
         if target.dtype != torch.float32:
             target = target.float()
@@ -101,8 +103,20 @@ class _FusedStepFn(torch.autograd.Function):
         summary = torch.empty((2 + 4 * n + sum(o[3] * o[3] for o in offs) + int(xchg_tail),), dtype=torch.float64, device=dev)
         Ks = (_I32 * n)(*tree.head_channels)
         Gs = (_I32 * n)(*[tree.group_count(L) for L in range(n)])
-        call("rhseg_step_finalize", ptr(ws), ptr(weights_all), B, n, Ks, Gs, float(smooth), n_pix, ptr(scal_all),
-             ptr(coef_all), ptr(summary), st)
+        call("rhseg_step_finalize", ptr(ws), ptr(weights_all), B, n, Ks, Gs, float(smooth), n_pix, (1 << n_active) - 1,
+             ptr(scal_all), ptr(coef_all), ptr(summary), st)
+        # data-parallel: the summary is summed over ranks BETWEEN forward and backward (a few hundred bytes), because the
+        # exact Dice gradient needs the global count of valid samples (dist.py, rhseg_dp_grad_scales)
+        n_summary = summary.numel() - int(xchg_tail)
+        ctx.dp = None
+        gsum = summary[:0]
+        if dp is not None:
+            reduce_fn, world = dp
+            gsum = reduce_fn(summary[:n_summary])
+            if gsum.data_ptr() == summary.data_ptr():
+                raise native.NativeError("the data-parallel summary reduction must not overwrite the local summary")
+            ctx.dp = (summary, gsum, int(world))
+        ctx.n_active = n_active
         conf, ratios, r_off = [], [], 2 + 4 * n
         for L in range(n):
             nc = offs[L][3]
@@ -114,7 +128,7 @@ class _FusedStepFn(torch.autograd.Function):
         ctx.save_for_backward(target, coef_all, *r["feats"], *r["head_w"], *r["film_w"], *r["logits"], *r["probs"],
                               *r["psums"], *r["eff_ws"], *[g for g in r["gbs"] if g is not None])
         ctx.set_materialize_grads(False)
-        outs = (scalars[0], scalars) + tuple(conf) + tuple(ratios) + tuple(r["probs"]) + tuple(r["logits"]) + (summary,)
+        outs = (scalars[0], scalars) + tuple(conf) + tuple(ratios) + tuple(r["probs"]) + tuple(r["logits"]) + (summary, gsum)
         ctx.mark_non_differentiable(*outs[1:])
         return outs
 
@@ -133,7 +147,7 @@ class _FusedStepFn(torch.autograd.Function):
         t_bs, t_cs, ch_off, esz = ctx.t_meta
         n_grads = 5 * n - 2
         if g_total is None:
-            return (None,) * (6 + n_grads)
+            return (None,) * (8 + n_grads)
         dev = feats[0].device
         st = stream_of(feats[0])
         tables = tree.device_tables(dev)
@@ -155,7 +169,14 @@ class _FusedStepFn(torch.autograd.Function):
         for k in tree.head_channels:
             coef_offs.append(coef_off)
             coef_off += B * k * 3
-        for L in range(n - 1, -1, -1):
+        g_ptrs = [(ptr(g), ptr(g))] * n
+        if ctx.dp is not None:  # per-level (g_ce, g_dice) = g * the factors that make DDP's mean over ranks exact
+            local, gsum, world = ctx.dp
+            scales = torch.empty((2 * n,), dtype=torch.float32, device=dev)
+            call("rhseg_dp_grad_scales", ptr(local), ptr(gsum), n, world, ptr(g), ptr(scales), st)
+            g_ptrs = [(scales.data_ptr() + 8 * L, scales.data_ptr() + 8 * L + 4) for L in range(n)]
+        # levels above the curriculum cap take no part in the loss: nothing reaches their logits (train.py:125-126)
+        for L in range(ctx.n_active - 1, -1, -1):
             K = tree.head_channels[L]
             K_prev = tree.head_channels[L - 1] if L > 0 else 0
             mode = tree.act_mode[L]
@@ -168,22 +189,22 @@ class _FusedStepFn(torch.autograd.Function):
             c_ptr = coef_all.data_ptr() + coef_offs[L] * 4
             if ctx.upsampled:
                 dz = bufs[L]["dz"]  # zeroed together with the weight sums: the band kernel adds into it
-                call("rhseg_head_dz_lowres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, ptr(g), ptr(g),
+                call("rhseg_head_dz_lowres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, g_ptrs[L][0], g_ptrs[L][1],
                      ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]), ptr(g_uniform), 1.0 / n_pix, ptr(dp_pix),
                      pix_mask, B, K, K_prev, Hf, Wf, H, W, mode | tree.group_hint(L), ptr(dz), ptr(dp_prev), None,
                      native.DZ_PREZEROED, st)
             else:
                 dz = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
-                call("rhseg_head_dz_fullres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, ptr(g), ptr(g),
+                call("rhseg_head_dz_fullres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, g_ptrs[L][0], g_ptrs[L][1],
                      ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]), ptr(g_uniform), 1.0 / n_pix, ptr(dp_pix),
                      pix_mask, B, K, K_prev, n_pix, mode, ptr(dz), ptr(dp_prev), st)
             d_feats[L], d_hw[L], d_hb[L], fw_g, fb_g, g_prev = level_weight_backward(
                 tree, L, ctx.dims, feats[L], dz, eff_ws[L], head_w[L], film_w[L - 1] if L > 0 else None, gbs[L],
-                psums[L - 1] if L > 0 else None, bufs[L], ctx.needs_input_grad[6 + L], st)
+                psums[L - 1] if L > 0 else None, bufs[L], ctx.needs_input_grad[8 + L], st)
             if L > 0:
                 d_fw[L - 1], d_fb[L - 1] = fw_g, fb_g
             g_uniform, dp_pix, pix_mask = g_prev, dp_prev, prev_mask
-        return (None,) * 6 + tuple(d_feats) + tuple(d_hw) + tuple(d_hb) + tuple(d_fw) + tuple(d_fb)
+        return (None,) * 8 + tuple(d_feats) + tuple(d_hw) + tuple(d_hb) + tuple(d_fw) + tuple(d_fb)
 
 
 class FusedHierStep:
@@ -209,6 +230,7 @@ class FusedHierStep:
         # free fp64 slots allocated behind StepOutput.summary (data-parallel jobs: set it to the number of
         # parameter-gradient elements that ride in the step's all-reduce, see dist.pack_exchange)
         self.exchange_tail = 0
+        self._dp = None
         if self.tree.num_levels > 8:
             raise native.NativeError("fused step supports trees up to 8 levels deep")
 
@@ -218,13 +240,26 @@ class FusedHierStep:
             self._weights[key] = torch.tensor(self._weights_host, dtype=torch.float32).to(device)
         return self._weights[key]
 
-    def __call__(self, feats, head_w, head_b, film_w, film_b, target, out_size: Optional[Tuple[int, int]] = None) -> StepOutput:
+    def data_parallel(self, reduce_fn, world: int):
+        """Batch-sharded training (one process per GPU): `reduce_fn(summary) -> new fp64 tensor` = SUM over ranks of the
+        step summary (e.g. `lambda s: px.all_reduce(s)` with a dist.PeerExchange, or a clone + torch.distributed.all_reduce).
+        It runs between forward and backward; the backward then scales each level's CE / Dice gradient so that DDP's mean
+        over ranks equals the single-process gradient on the concatenated batch, also when the ranks hold different
+        numbers of dice-valid samples (Metrics/losses.py:64-66).  reduce_fn=None switches it off."""
+        self._dp = None if reduce_fn is None else (reduce_fn, int(world))
+
+    def __call__(self, feats, head_w, head_b, film_w, film_b, target, out_size: Optional[Tuple[int, int]] = None,
+                 level_cap: Optional[int] = None) -> StepOutput:
+        """level_cap: the reference's level-pretrain curriculum (train.get_loss, train.py:121-126): only levels
+        L <= level_cap = min(n-1, cur_epoch // pretrain_epoch) enter the loss and receive gradients; every level's
+        CE / Dice value, metrics and the consistency term are still reported.  None = all levels."""
         n = self.tree.num_levels
         if not (len(feats) == len(head_w) == len(head_b) == n and len(film_w) == len(film_b) == n - 1):
             raise native.NativeError("expected %d levels of features/heads and %d FiLMs" % (n, n - 1))
-        outs = _FusedStepFn.apply(self.tree, out_size, self.weights(feats[0].device), self.smooth, self.exchange_tail,
-                                  target, *feats, *head_w, *head_b, *film_w, *film_b)
-        xbuf = outs[2 + 4 * n]
+        with torch.cuda.device(feats[0].device):  # kernels launch on the tensors' device, whatever the current one is
+            outs = _FusedStepFn.apply(self.tree, out_size, self.weights(feats[0].device), self.smooth, self.exchange_tail,
+                                      level_cap, self._dp, target, *feats, *head_w, *head_b, *film_w, *film_b)
+        xbuf, gsum = outs[2 + 4 * n], outs[3 + 4 * n]
         return StepOutput(outs[0], outs[1], list(outs[2:2 + n]), list(outs[2 + n:2 + 2 * n]),
                           list(outs[2 + 2 * n:2 + 3 * n]), list(outs[2 + 3 * n:2 + 4 * n]), n,
-                          xbuf[:xbuf.numel() - self.exchange_tail], xbuf)
+                          xbuf[:xbuf.numel() - self.exchange_tail], xbuf, gsum if gsum.numel() else None)

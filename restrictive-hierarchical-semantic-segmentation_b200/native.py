@@ -41,6 +41,7 @@ SIGNATURES = {
     "rhseg_xchg_connect": [_P, _I, _P],
     "rhseg_xchg_all_reduce": [_P, _P, _L, _P, _P, _I, _P, _P],
     "rhseg_xchg_status": [_P, _P],
+    "rhseg_xchg_set_timeout_ms": [_P, _L],
     "rhseg_xchg_destroy": [_P],
     "rhseg_head_conv_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "rhseg_head_conv_bwd_params": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _D, _I, _P, _P, _P, _P, _P, _P, _P],
@@ -53,7 +54,8 @@ SIGNATURES = {
     "rhseg_metric_ratios": [_P, _I, _P, _P],
     "rhseg_predict_onehot": [_P, _P, _L, _L, _I, _I, _I, _P, _P, _P, _P],
     "rhseg_head_dz_fullres_fused": [_P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _D, _P, _U, _I, _I, _I, _I, _I, _P, _P, _P],
-    "rhseg_step_finalize": [_P, _P, _I, _I, _P, _P, _D, _L, _P, _P, _P, _P],
+    "rhseg_step_finalize": [_P, _P, _I, _I, _P, _P, _D, _L, _U, _P, _P, _P, _P],
+    "rhseg_dp_grad_scales": [_P, _P, _I, _I, _P, _P, _P],
     "rhseg_level_eval": [_P, _P, _L, _L, _P, _L, _L, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
     "rhseg_concat_image_logits": [_P, _I, _P, _I, _I, _I, _P, _P],
     "rhseg_stitch_levels": [_P, _I, _I, _I, _P, _I, _P, _P],
