@@ -184,7 +184,8 @@ int rhseg_head_conv_bwd(const float* feats, const float* dz, const float* eff_w,
  * zeroed here); n_pix_out = H*W of the output (the FiLM pool size); ticket = a device counter that is zero on entry (left
  * zero).  Two forms, same results: conv kernel + 12-CTA parameter kernel behind a programmatic dependent launch
  * (default, measured faster for C = 720), or the parameter gradients as the tail of the conv kernel's last CTA
- * (RHSEG_PARAM_TAIL=1).                                                                                        */
+ * (library built with -DRHSEG_WITH_PARAM_TAIL and RHSEG_PARAM_TAIL=1; compiled out by default because the tail costs
+ * the conv kernel registers and, for 16-byte-aligned planes, its second CTA per SM).                              */
 int rhseg_head_conv_bwd_params(const float* feats, const float* dz, const float* eff_w, int B, int C, int K,
                                int n_pix, float* dfeats, double* S, double* s, int flags, const float* head_w,
                                const float* film_w, const float* gamma_beta, const double* prev_psum,

@@ -363,25 +363,7 @@ def stitch_flat_to_levels(flat, tree: dict):
 # synthetic inputs — shared by tests, smoke and bench
 # --------------------------------------------------------------------------
 def synth_targets(levels, groups, B, H, W, gen: torch.Generator, blobs: bool = False, device="cpu"):
-    """Ternary {1,0,-1} targets per level following Data/dataset.py:227-265
-    (process_ignore_values): 1 on the class, 0 inside the direct parent, -1 outside it."""
-    K0 = len(levels[0])
-    if blobs:
-        coarse = torch.randint(0, K0, (B, 1, max(H // 4, 1), max(W // 4, 1)), generator=gen).float()
-        lab = F.interpolate(coarse, size=(H, W), mode="nearest").long().squeeze(1)
-    else:
-        lab = torch.randint(0, K0, (B, H, W), generator=gen)
-    out = [F.one_hot(lab, K0).permute(0, 3, 1, 2).float()]
-    for L in range(1, len(levels)):
-        t = torch.full((B, len(levels[L]), H, W), -1.0)
-        start = 0
-        for pname, kids in groups[L - 1]:
-            g = len(kids)
-            pi = levels[L - 1].index(pname)
-            inside = out[L - 1][:, pi] == 1
-            lab = torch.randint(0, g, (B, H, W), generator=gen)
-            oh = F.one_hot(lab, g).permute(0, 3, 1, 2).float()
-            t[:, start:start + g] = torch.where(inside.unsqueeze(1), oh, torch.full_like(oh, -1.0))
-            start += g
-        out.append(t)
-    return [o.to(device) for o in out]
+    """Ternary {1,0,-1} targets per level following Data/dataset.py:227-265 (process_ignore_values).  The generator lives
+    in the neutral module tools/synth.py (bench.py's product arm uses it without importing the oracle)."""
+    from tools import synth
+    return synth.synth_targets(levels, groups, B, H, W, gen, blobs=blobs, device=device)

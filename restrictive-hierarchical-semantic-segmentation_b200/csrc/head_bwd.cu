@@ -447,6 +447,10 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
     advance();
   }
   if (cur_seg >= 0) flush();
+#ifdef RHSEG_WITH_PARAM_TAIL
+  // Compiled out by default: measured slower than the separate 12-CTA kernel (25 us against 8.6 us at C = 720), and the
+  // call into the tail raised the 128-bit instance of this kernel from 96 to 128 registers, i.e. from two CTAs per SM
+  // to one (UNet conv backward 0.81 -> 0.75 of the HBM peak).
   if (pt.ticket != nullptr) {
     // last CTA done: S / s are complete -> parameter gradients (the ring is free: its memory holds the pool-gradient sums)
     __shared__ int is_last;
@@ -460,6 +464,7 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
       if (tid == 0) *pt.ticket = 0u;  // ready for the next launch / graph replay
     }
   }
+#endif
 }
 
 template <int K, int VEC, int J, typename CFG>
@@ -683,7 +688,11 @@ extern "C" int rhseg_head_conv_bwd_params(const float* feats, const float* dz, c
   // rhseg_head_param_grads kernel behind a programmatic dependent launch, so the two-kernel form is the default;
   // RHSEG_PARAM_TAIL=1 selects the tail (kept for small C / B where one CTA is enough).
   static int use_tail = -1;
+#ifdef RHSEG_WITH_PARAM_TAIL
   if (use_tail < 0) { const char* e = getenv("RHSEG_PARAM_TAIL"); use_tail = (e && e[0] == '1') ? 1 : 0; }
+#else
+  use_tail = 0;
+#endif
   if (!use_tail || (film_w && ((long)B * K_prev + 2L * B * C) * 8 > 60 * 1024)) {
     ParamTail none{};
     const int rc = conv_bwd_impl(feats, dz, eff_w, B, C, K, n_pix, dfeats, S, s, flags, stream, none);

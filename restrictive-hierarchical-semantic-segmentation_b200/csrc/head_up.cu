@@ -488,10 +488,10 @@ static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32
 #define RHSEG_BAND(VEC, EK, GS) rc = launch_band<K, VEC, MODE, EK, GS>(z_lo, prev_probs, table, B, Hf, Wf, H, W, K_prev, sy, sx, logits, probs, psum, st, e, &done)
 #define RHSEG_BAND_V(EK, GS)                                  \
       do {                                                    \
-        if constexpr (K <= 4) {                               \
-          if (v4) RHSEG_BAND(4, EK, GS);                      \
+        if (v4) RHSEG_BAND(4, EK, GS);                        \
+        if constexpr (K <= 4) { /* 2 px / thread needs > 256 threads for wide rows: too few registers for K > 4 (spills) */ \
+          if (!done && rc == RHSEG_OK && v2) RHSEG_BAND(2, EK, GS); \
         }                                                     \
-        if (!done && rc == RHSEG_OK && v2) RHSEG_BAND(2, EK, GS); \
       } while (0)
       if constexpr (MODE == RHSEG_ACT_SIGMOID) {
         if (evalk == 0) RHSEG_BAND_V(0, K); else RHSEG_BAND_V(1, K);
@@ -500,7 +500,9 @@ static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32
         if (single) {
           if (evalk == 0) RHSEG_BAND_V(0, K); else if (evalk == 1) RHSEG_BAND_V(1, K); else RHSEG_BAND_V(2, K);
         } else {
-          if (evalk == 0) RHSEG_BAND_V(0, 0); else if (evalk == 1) RHSEG_BAND_V(1, 0); else RHSEG_BAND_V(2, 0);
+          if (evalk == 0) RHSEG_BAND_V(0, 0);
+          else if constexpr (K <= 6) { if (evalk == 1) RHSEG_BAND_V(1, 0); else RHSEG_BAND_V(2, 0); }
+          // K > 6 with a table-driven group layout and the fused evaluation would spill: generic kernel + rhseg_level_eval
         }
       }
 #undef RHSEG_BAND_V

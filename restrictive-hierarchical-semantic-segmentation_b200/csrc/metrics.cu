@@ -518,20 +518,23 @@ extern "C" int rhseg_level_eval(const float* logits, const float* targets, long 
         if (cons_in) return launch_eval_pipe<KK, 2, KK>(logits, targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, table, B, N, stats, cons, conf, idx_out, st);
         return launch_eval_pipe<KK, 1, KK>(logits, targets, t_bstride, t_cstride, nullptr, 0, 0, nullptr, table, B, N, stats, cons, conf, idx_out, st);
       }
-      if (cons_in) return launch_eval_pipe<KK, 2, 0>(logits, targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, table, B, N, stats, cons, conf, idx_out, st);
+      if (cons_in) {
+        // table-driven group layout + consistency with K > 6 would spill in the pipelined kernel: generic kernel below
+        if constexpr (KK <= 6) return launch_eval_pipe<KK, 2, 0>(logits, targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, table, B, N, stats, cons, conf, idx_out, st);
+      } else
       return launch_eval_pipe<KK, 1, 0>(logits, targets, t_bstride, t_cstride, nullptr, 0, 0, nullptr, table, B, N, stats, cons, conf, idx_out, st);
     });
   }
   // generic path: any alignment, any size (level kind decided at run time)
   const int slots = std::max(1, device_sm_count() * 2 / B);  // CTAs per sample for one resident wave
   RHSEG_DISPATCH_K(K, {
-    if (v4) {
+    if (v4 && KK <= 4) {  // 4 pixels per thread spill beyond K = 4 at two CTAs per SM: wider levels take one pixel per thread
       dim3 grid((unsigned)balanced_grid((N + THREADS * 4 - 1) / (THREADS * 4), slots), B);
-      launch_pdl(level_eval_kernel<KK, 4, 2, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
+      launch_pdl(level_eval_kernel<(KK <= 4 ? KK : 1), 4, 2, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
           pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     } else {
       dim3 grid((unsigned)balanced_grid((N + THREADS - 1) / THREADS, slots), B);
-      launch_pdl(level_eval_kernel<KK, 1, 2, THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
+      launch_pdl(level_eval_kernel<KK, 1, (KK > 6 ? 1 : 2), THREADS>, dim3(grid), dim3(THREADS), 0, st, logits, targets, t_bstride, t_cstride, parent_targets,
           pt_bstride, pt_cstride, prev_idx, table, N, child, stats, cons, conf, idx_out);
     }
   });

@@ -663,17 +663,18 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int hint, i
 #define RHSEG_DZB(VEC, ACTK, GS) rc = launch_dz_band<K, VEC, SRC, MODE, ACTK, GS>(dz_hi, fa, B, Hf, Wf, H, W, sy, sx, dz_lo, st, &done)
 #define RHSEG_DZB_V(ACTK, GS)                                   \
       do {                                                      \
-        if constexpr (K <= 4) {                                 \
-          if (tune_vec != 2) RHSEG_DZB(4, ACTK, GS);            \
+        if (tune_vec != 2 || K > 4) RHSEG_DZB(4, ACTK, GS);     \
+        if constexpr (K <= 4) { /* 2 px / thread: up to 416 threads, too few registers for K > 4 (spills) */ \
+          if (!done && rc == RHSEG_OK) RHSEG_DZB(2, ACTK, GS);  \
         }                                                       \
-        if (!done && rc == RHSEG_OK) RHSEG_DZB(2, ACTK, GS);    \
       } while (0)
       if constexpr (SRC == 0) {
         RHSEG_DZB_V(1, K);
       } else if constexpr (MODE == RHSEG_ACT_SIGMOID) {
         if (no_act) RHSEG_DZB_V(1, K); else if (unif) RHSEG_DZB_V(2, K); else RHSEG_DZB_V(0, K);
       } else {
-        if (no_act) RHSEG_DZB_V(1, K); else if (hint == K) RHSEG_DZB_V(0, K); else RHSEG_DZB_V(0, 0);
+        if (no_act) RHSEG_DZB_V(1, K); else if (hint == K) RHSEG_DZB_V(0, K);
+        else if constexpr (K <= 5) RHSEG_DZB_V(0, 0);  // table-driven group layout with K > 5 would spill: tiled kernel below
       }
 #undef RHSEG_DZB_V
 #undef RHSEG_DZB

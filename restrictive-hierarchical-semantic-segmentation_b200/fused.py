@@ -263,3 +263,85 @@ class FusedHierStep:
         return StepOutput(outs[0], outs[1], list(outs[2:2 + n]), list(outs[2 + n:2 + 2 * n]),
                           list(outs[2 + 2 * n:2 + 3 * n]), list(outs[2 + 3 * n:2 + 4 * n]), n,
                           xbuf[:xbuf.numel() - self.exchange_tail], xbuf, gsum if gsum.numel() else None)
+
+
+class _FusedFlatFn(torch.autograd.Function):
+    """Flat model (model_type 0; Models/models.py:258-261, :754-757): weighted CE + Dice on the logits of ONE level of
+    leaf classes, the train-path prediction and the confusion-matrix metrics, in three launches: rhseg_level_eval
+    (statistics + bit-exact argmax(softmax) + confusion, one pass over logits and targets), rhseg_step_finalize,
+    and rhseg_head_dz_fullres_fused in the backward (closed-form gradient, one pass)."""
+
+    @staticmethod
+    def forward(ctx, tree: ClassTree, weights, smooth, logits, target):
+        native.require_cuda(logits, target)
+        if logits.dtype != torch.float32:
+            raise native.NativeError("flat step expects float32 logits, got %s" % logits.dtype)
+        z = logits if logits.is_contiguous() else logits.contiguous()
+        t = target if target.dtype == torch.float32 else target.float()
+        if not (t.stride(3) == 1 and t.stride(2) == t.shape[3]):
+            t = t.contiguous()
+        B, K, H, W = z.shape
+        if tuple(t.shape) != tuple(z.shape) or K != tree.head_channels[0]:
+            raise native.NativeError("flat step: logits %s / targets %s / %d classes do not match"
+                                     % (tuple(z.shape), tuple(t.shape), tree.head_channels[0]))
+        dev, st = z.device, stream_of(z)
+        n_pix = H * W
+        offs, words = _eval_layout(tree, B)
+        ws = torch.zeros((words,), dtype=torch.float64, device=dev)
+        tables = tree.device_tables(dev)
+        call("rhseg_level_eval", ptr(z), ptr(t), t.stride(0), t.stride(1), None, 0, 0, None, ptr(tables[0]), B, K, n_pix, 0,
+             ptr(ws), None, 1, st)
+        scal_all = torch.empty((2 + 4 + 5 * K,), dtype=torch.float32, device=dev)
+        coef = torch.empty((B * K * 3,), dtype=torch.float32, device=dev)
+        summary = torch.empty((2 + 4 + K * K,), dtype=torch.float64, device=dev)
+        Ks, Gs = (_I32 * 1)(K), (_I32 * 1)(0)
+        call("rhseg_step_finalize", ptr(ws), ptr(weights), B, 1, Ks, Gs, float(smooth), n_pix, 1, ptr(scal_all), ptr(coef),
+             ptr(summary), st)
+        conf = ws[offs[0][2]:offs[0][2] + K * K].view(torch.int64).view(K, K)
+        ratios = scal_all[6:6 + 5 * K].view(5, K)
+        ctx.save_for_backward(z, t, coef, tables[0])
+        ctx.set_materialize_grads(False)
+        outs = (scal_all[0], scal_all[:6], conf, ratios, summary)
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_total, *_unused):
+        if g_total is None:
+            return None, None, None, None, None
+        z, t, coef, table = ctx.saved_tensors
+        B, K, H, W = z.shape
+        g = g_total.reshape(1)
+        g = g if g.dtype == torch.float32 else g.float()
+        dz = torch.empty_like(z)
+        call("rhseg_head_dz_fullres_fused", ptr(z), ptr(t), t.stride(0), t.stride(1), ptr(coef), ptr(g), ptr(g), None, ptr(table),
+             None, 1.0 / (H * W), None, 0, B, K, 0, H * W, native.ACT_SIGMOID, ptr(dz), None, stream_of(z))
+        return None, None, None, dz, None
+
+
+class FusedFlatStep:
+    """Loss + metrics of the flat baseline (BASELINE.json configs[3]: model_type 0, 7 leaf classes, README.md:79 weights):
+
+        step = FusedFlatStep(class_names_or_count, class_weight)
+        out = step(logits, target)          # logits [B,K,H,W] from the donor's flat head, target {0,1} one-hots
+        out.loss.backward()                 # d(CE + Dice)/d logits
+
+    Same numbers as CrossEntropyLoss + SoftDiceLoss (Metrics/losses.py) and the five metric wrappers called the way
+    train.py calls them for a flat model, without one-hot tensors and without a host sync."""
+
+    def __init__(self, classes, class_weight: Sequence[float], smooth: float = 0.0):
+        names = ["c%d" % i for i in range(classes)] if isinstance(classes, int) else list(classes)
+        if len(class_weight) != len(names):
+            raise ValueError("%d classes but %d weights" % (len(names), len(class_weight)))
+        self.tree = ClassTree({n: {} for n in names})
+        self._weights_host = [float(x) for x in class_weight]
+        self._weights = {}
+        self.smooth = float(smooth)
+
+    def __call__(self, logits, target) -> StepOutput:
+        key = str(logits.device)
+        if key not in self._weights:
+            self._weights[key] = torch.tensor(self._weights_host, dtype=torch.float32).to(logits.device)
+        with torch.cuda.device(logits.device):
+            loss, scalars, conf, ratios, summary = _FusedFlatFn.apply(self.tree, self._weights[key], self.smooth, logits, target)
+        return StepOutput(loss, scalars, [conf], [ratios], [None], [logits], 1, summary, summary)

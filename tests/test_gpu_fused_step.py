@@ -95,38 +95,6 @@ def test_fused_step_equals_dropin_modules(name):
             close(x.grad, y.grad, rtol=2e-6, what=name)
 
 
-def test_fused_step_full_size_hrnet_against_oracle_sample():
-    """BASELINE.json configs[1] shape (HRNet-W48 tl, 620x620): one sample against the oracle on CPU."""
-    import rhseg_b200
-    import bench
-    wl = dict(bench.WORKLOADS["hrnet_w48_tl_620_b4"])
-    data = bench.synth_inputs(wl, 1, seed=3, device="cpu")
-    h = data["host"]
-    leaves_ref = [[t.clone().requires_grad_(True) for t in h[k]] for k in ("feats", "hw", "hb", "fw", "fb")]
-    levels, parent_of, groups = data["levels"], data["parent_of"], data["groups"]
-    probs, logits = O.head_forward(*leaves_ref, levels, groups, (620, 620))
-    targets, s = [], 0
-    for k in data["chans"]:
-        targets.append(h["target"][:, s:s + k]); s += k
-    onehots, eval_t = O.predict_onehot_masked([z.detach() for z in logits], targets)
-    loss_ref, _ = O.total_loss(logits, targets, data["weights"], onehots, levels, parent_of)
-    loss_ref.backward()
-    step = rhseg_b200.FusedHierStep(wl["tree"], data["weights"])
-    leaves = [[t.clone().to(DEV).requires_grad_(True) for t in h[k]] for k in ("feats", "hw", "hb", "fw", "fb")]
-    out = step(*leaves, h["target"].to(DEV), (620, 620))
-    out.loss.backward()
-    assert abs(out.loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
-    for L in range(2):
-        # argmax-derived integers: compare on the device's own logits (the conv reduction order differs
-        # from ATen's by ~1e-7, which may flip exact near-ties)
-        oh_dev, et_dev = O.predict_onehot_masked([out.logits[L].cpu()], [targets[L]])
-        assert torch.equal(out.confusion[L].cpu(), O.level_confusion(oh_dev[0], et_dev[0], 4, L != 0))
-        close(out.logits[L], logits[L], what=f"logits{L}")
-        close(leaves[0][L].grad, leaves_ref[0][L].grad, what=f"dfeats{L}")
-        close(leaves[1][L].grad, leaves_ref[1][L].grad, rtol=2e-5, what=f"dhead_w{L}")
-    close(leaves[3][0].grad, leaves_ref[3][0].grad, rtol=2e-5, what="dfilm_w0")
-
-
 def test_fused_step_summary_matches_pack_layout():
     """StepOutput.summary (written by rhseg_step_finalize) == dist.pack_step_summary of the same step."""
     from rhseg_b200 import dist as rdist
@@ -223,4 +191,4 @@ def test_fused_step_replays_from_a_cuda_graph():
         for a, b in zip(got[1], e_out.confusion):
             assert torch.equal(a, b)
         for i, (a, b) in enumerate(zip(got[2], e_grads)):
-            close(a, b, rtol=2e-5, what="graph grad %d/%d" % (it, i))
+            close(a, b, rtol=1e-6, what="graph grad %d/%d" % (it, i))  # same kernels: only the order of fp64 atomics differs

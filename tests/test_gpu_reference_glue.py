@@ -57,6 +57,10 @@ def test_reference_train_epoch_runs_on_the_dropin_modules(dropin_train, name):
     out = glue.run_epoch(train, model, losses, metric_objs, batches, meta["tree"], torch.device(DEV), meta["pretrain"],
                          meta["epoch_num"], meta["lr"])
     got = glue.pack_result(out)
+    # Tolerances of this test only: the golden epoch ran its donor 3x3 convolution in oneDNN on the CPU, this one in cuDNN
+    # (features differ by ~1e-6 relative before the head is reached), and the values below are means over three batches
+    # AFTER optimiser steps, so that difference compounds through two SGD updates: 2e-5 instead of 1e-5.  The head / loss
+    # kernels themselves are held to 1e-5 on identical inputs in test_reference_get_loss_and_get_metrics_on_dropin_outputs.
     assert abs(got["loss"] - z["loss"]) <= 2e-5 * abs(z["loss"]), (got["loss"], z["loss"])
     np.testing.assert_allclose(got["level_loss"], z["level_loss"], rtol=2e-5, atol=1e-7)
     # metrics are ratios of pixel counts: identical unless a near-tie pixel flips between the CPU and GPU donors

@@ -146,14 +146,19 @@ def test_text_tree_utilities(tmp_path):
 def test_bench_byte_model_matches_survey():
     import bench
     wl = bench.WORKLOADS["unet_tl_620_b4"]
-    alg = bench.algorithmic_bytes(wl, [4, 4], [0, 1], 4)
+    alg = bench.algorithmic_bytes(wl, 4)
     assert abs(alg["step"] / 1e9 - 2.669) < 0.002 and abs(alg["metrics"] / 1e9 - 0.098) < 0.001
     wl = bench.WORKLOADS["hrnet_w48_tl_620_b4"]
-    alg = bench.algorithmic_bytes(wl, [4, 4], [0, 1], 4)
+    alg = bench.algorithmic_bytes(wl, 4)
     assert abs(alg["step"] / 1e9 - 1.968) < 0.002
     wl = bench.WORKLOADS["hrnet_w48_ext_620_b4"]
-    alg = bench.algorithmic_bytes(wl, [2, 2, 4, 3], [0, 1, 2, 1], 4)
+    alg = bench.algorithmic_bytes(wl, 4)
     assert abs(alg["step"] / 1e9 - 3.776) < 0.003
+    assert bench.tree_shape(wl)[2:] == ([2, 2, 4, 3], [0, 1, 2, 1])
+    alg = bench.algorithmic_bytes(bench.WORKLOADS["flat7_620_b4"], 4)   # 140 B/px + 56 B/px metrics
+    assert abs(alg["step"] / 1e9 - 0.215) < 0.001 and abs(alg["metrics"] / 1e9 - 0.086) < 0.001
+    alg = bench.algorithmic_bytes(bench.WORKLOADS["unet_tl_1024_b64"], 64)  # row 5: 116.5 GB in total
+    assert abs(alg["step"] / 1e9 - 116.5) < 0.1
 
 
 def _free_port():
