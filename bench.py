@@ -631,7 +631,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
 
     # ---- the same step through the drop-in modules (reference call sequence), eager ----
-    dropin_ms = None
+    dropin_ms = dropin_graph_ms = None
     if not args.no_dropin and not st.flat and not wl.get("strong"):
         for _ in range(3):
             st.step_dropin()
@@ -647,6 +647,33 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             ts.append(d0.elapsed_time(d1) / reps)
         dropin_ms = statistics.median(ts)
+        # the same call sequence replayed from a CUDA graph (what a caller gets who captures the loop body: no host work)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                st.step_dropin()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            dg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(dg):
+                st.step_dropin()
+            dg.replay()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                d0.record()
+                for _ in range(reps):
+                    dg.replay()
+                d1.record()
+                torch.cuda.synchronize()
+                ts.append(d0.elapsed_time(d1) / reps)
+            dropin_graph_ms = statistics.median(ts)
+            del dg
+        except Exception as e:
+            sys.stderr.write("drop-in route not capturable (%r)\n" % (e,))
+            torch.cuda.synchronize()
 
     # ---- dominant-kernel timing, live, on the launching stream (eager steps, inputs > L2) ----
     nL = len(hz.data["chans"])
@@ -723,7 +750,9 @@ def run_ours(args, rank, world, local_rank):
         line["e2e"] = e2e
     if dropin_ms is not None:
         line["dropin_modules"] = {"ms_per_step": dropin_ms, "value": B * wl["H"] * wl["W"] / (dropin_ms * 1e-3) / 1e6, "unit": "Mpixel/s",
-                                  "note": "same step through Models/Metrics drop-in modules in the reference's call order, eager, this rank"}
+                                  "cuda_graph_ms_per_step": dropin_graph_ms,
+                                  "cuda_graph_value": (B * wl["H"] * wl["W"] / (dropin_graph_ms * 1e-3) / 1e6) if dropin_graph_ms else None,
+                                  "note": "same step through Models/Metrics drop-in modules in the reference's call order, this rank: eager (host-bound: ~40 launches + autograd + allocator per step) and the same calls replayed from a CUDA graph"}
     if check is not None:
         line["dp_check"] = check
     if not args.no_configs and not args.workload_only:

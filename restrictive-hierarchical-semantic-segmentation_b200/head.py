@@ -9,6 +9,7 @@ Backward runs last level -> first (closed forms in DESIGN.md): the gradient reac
 P_{L-1} is a per-(sample, channel) constant from the FiLM pool plus, for trees deeper than two
 levels, a per-pixel term from the composition.
 """
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -25,6 +26,9 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 _SIDE_STREAMS = {}
+# development switch: upsampled heads evaluate EVERY level inside its hi-res forward kernel (default: only the last one;
+# the others run rhseg_level_eval on a side stream, concurrent with the next level's forward -- measured faster)
+_FUSE_EVAL_ALL = os.environ.get("RHSEG_FUSE_EVAL_ALL", "0") == "1"
 
 
 def _side_stream(dev):
@@ -107,7 +111,7 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words
         # The evaluation of level L only needs its logits (and the previous level's index map): for all
         # but the last level it runs on a side stream, overlapping the (memory-bound) forward of the next
         # level; the last level's evaluation is fused into its hi-res forward kernel when there is one.
-        overlap = ev is not None and L < n - 1
+        overlap = ev is not None and L < n - 1 and not (upsampled and _FUSE_EVAL_ALL)
         if ev is not None and upsampled and not overlap:
             t_ptr, t_bs, t_cs, pt_ptr, pidx_ptr, words_ptr, idx_ptr = ev
             if used_side:  # the previous level's index map is produced on the side stream
