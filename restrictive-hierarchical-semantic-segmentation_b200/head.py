@@ -26,9 +26,11 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 _SIDE_STREAMS = {}
-# development switch: upsampled heads evaluate EVERY level inside its hi-res forward kernel (default: only the last one;
-# the others run rhseg_level_eval on a side stream, concurrent with the next level's forward -- measured faster)
-_FUSE_EVAL_ALL = os.environ.get("RHSEG_FUSE_EVAL_ALL", "0") == "1"
+# Upsampled heads, fused training step: which levels are evaluated INSIDE their hi-res forward kernel
+# (rhseg_head_level_fwd_eval) instead of by rhseg_level_eval on a side stream, concurrent with the next level's forward.
+#   "last": only the last level (nothing is left to overlap with)     "root": also level 0     "all": every level
+# Measured: HRNet-W48 tl "root" = "all" 0.420 ms vs "last" 0.428 ms; extended tree "all" is slower than "last".
+_FUSE_EVAL = os.environ.get("RHSEG_FUSE_EVAL", "root")
 
 
 def _side_stream(dev):
@@ -111,7 +113,7 @@ def forward_levels(tree: ClassTree, out_size, tensors, evaluate=None, zero_words
         # The evaluation of level L only needs its logits (and the previous level's index map): for all
         # but the last level it runs on a side stream, overlapping the (memory-bound) forward of the next
         # level; the last level's evaluation is fused into its hi-res forward kernel when there is one.
-        overlap = ev is not None and L < n - 1 and not (upsampled and _FUSE_EVAL_ALL)
+        overlap = ev is not None and L < n - 1 and not (upsampled and (_FUSE_EVAL == "all" or (_FUSE_EVAL == "root" and L == 0)))
         if ev is not None and upsampled and not overlap:
             t_ptr, t_bs, t_cs, pt_ptr, pidx_ptr, words_ptr, idx_ptr = ev
             if used_side:  # the previous level's index map is produced on the side stream

@@ -9,7 +9,8 @@ import threading
 import torch
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "librhseg_b200.so")
+# RHSEG_LIB: development only -- A/B of two builds inside one GPU call (tools/ab.sh); the product is the in-tree library
+LIB_PATH = os.environ.get("RHSEG_LIB") or os.path.join(PKG_DIR, "librhseg_b200.so")
 
 MAX_K = 16
 KERNEL_MAX_K = 8
