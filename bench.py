@@ -573,12 +573,47 @@ def dominant_alone(hz, alg):
     return {"kernel": name, "ms": ms, "bytes": nbytes, "frac": lambda peak: nbytes / (ms * 1e-3) / 1e9 / peak}
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pins this process (and with it the first-touch placement of its pinned host buffers) to the NUMA node its GPU
+    hangs off, so that the end-to-end H2D copies do not cross the socket interconnect.  Best effort; returns what it did."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        info["pci"] = bdf
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["numa_node"], info["cpus"] = node, len(allowed)
+    except Exception as e:
+        info["error"] = repr(e)[:80]
+    return info
+
+
+def gpu_topology():
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        return [l.rstrip() for l in out.splitlines() if l.strip() and not l.startswith(("Legend", "  "))][:12]
+    except Exception:
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     from rhseg_b200 import native
     name = args.workload
     wl = WORKLOADS[name]
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else None
     peaks, peak_src = load_peaks()
     check = dp_check(args, rank, world, dev) if (world > 1 and not args.no_dp_check) else None
 
@@ -721,7 +756,7 @@ def run_ours(args, rank, world, local_rank):
                 "cuda_graph": graph_used, "loss": loss_value,
                 "collective": ("summary all-reduce between fwd and bwd + head/FiLM gradient all-reduce after bwd, %s"
                                % {"p2p": "one peer-memory kernel over NVLink each (rhseg_xchg_all_reduce)", "nccl": "NCCL"}[hz.kind]) if world > 1 else "none",
-                "xchg_status": xchg_status},
+                "xchg_status": xchg_status, "numa": numa, "topology": gpu_topology() if world > 1 else None},
         "step_bytes": {"algorithmic_head_loss_fwd_bwd": alg["step"], "metrics": alg["metrics"],
                        "frac_of_hbm_peak_head_loss_fwd_bwd": alg["step"] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                        "frac_of_hbm_peak_whole_step": (alg["step"] + alg["metrics"]) / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
@@ -777,14 +812,18 @@ def time_e2e(args, hz):
     host = data["host"]
     flat = st.flat
     src_feats = [host["logits"]] if flat else host["feats"]
-    h2d = sum(f.numel() * 4 for f in src_feats) + host["target"].numel() * 4
+    # the ternary targets travel as int8 (the values the dataset produces: 1, 0, -1) and are widened on the device by
+    # rhseg_targets_i8_to_f32 inside the step: a quarter of their fp32 bytes over PCIe
+    tgt_host = host["target"].to(torch.int8).pin_memory()
+    h2d = sum(f.numel() * 4 for f in src_feats) + tgt_host.numel()
     nres = 6 if flat else 2 + 4 * len(data["chans"])
     out_host = torch.empty(nres + sum(5 * (k + (1 if L else 0)) for L, k in enumerate(data["chans"])), dtype=torch.float32).pin_memory()
     d2h = out_host.numel() * 4
     cur_feats = [st.logits] if flat else st.feats
     # two device-side input sets: the H2D copy of step i+1 runs on a copy stream while step i computes
-    sets = [(cur_feats, st.target),
-            ([torch.empty_like(f).requires_grad_(True) for f in cur_feats], torch.empty_like(st.target))]
+    target_f32 = st.target
+    sets = [(cur_feats, torch.empty(st.target.shape, dtype=torch.int8, device=dev)),
+            ([torch.empty_like(f).requires_grad_(True) for f in cur_feats], torch.empty(st.target.shape, dtype=torch.int8, device=dev))]
     copy_stream = torch.cuda.Stream()
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -796,7 +835,7 @@ def time_e2e(args, hz):
             with torch.no_grad():
                 for dst, src in zip(feats_i, src_feats):
                     dst.copy_(src, non_blocking=True)
-                target_i.copy_(host["target"], non_blocking=True)
+                target_i.copy_(tgt_host, non_blocking=True)
             ready[i % 2].record(copy_stream)
 
     def e2e_step(i):
@@ -818,7 +857,7 @@ def time_e2e(args, hz):
     for i in range(2):
         e2e_step(i)
     e2e_steps = max(3, min(args.steps, 30))
-    blocks, i = [], 2
+    blocks, own, i = [], [], 2
     for _ in range(3):
         hz.barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -830,19 +869,27 @@ def time_e2e(args, hz):
         hz.barrier()
         copy_stream.synchronize()
         t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        own.append(t.item() / e2e_steps)
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         blocks.append(t.item() / e2e_steps)
     if flat:
-        st.logits, st.target = sets[0][0][0], sets[0][1]
+        st.logits, st.target = sets[0][0][0], target_f32
     else:
-        st.feats, st.target = sets[0]
+        st.feats, st.target = sets[0][0], target_f32
     e2e_ms = statistics.median(blocks)
+    per_rank = [statistics.median(own)]
+    if world > 1:
+        allr = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        torch.distributed.all_gather(allr, torch.tensor([per_rank[0]], dtype=torch.float64, device=dev))
+        per_rank = [t.item() for t in allr]
     px_total = sum(local_batch(hz.wl, world, r) for r in range(world)) * hz.wl["H"] * hz.wl["W"]
     return {"value": px_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps, "blocks": len(blocks),
             "h2d_GBps_per_gpu": h2d / (e2e_ms * 1e-3) / 1e9,
-            "note": "features+targets copied from pinned host memory every step (copy of step i+1 overlaps step i); PCIe-bound"}
+            "h2d_GBps_per_rank": [h2d / (m * 1e-3) / 1e9 for m in per_rank],
+            "note": "features (fp32) + ternary targets (int8, widened on the device) copied from pinned host memory every step "
+                    "(copy of step i+1 overlaps step i); PCIe-bound"}
 
 
 def load_peaks():

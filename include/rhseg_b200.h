@@ -332,6 +332,11 @@ int rhseg_stitch_levels(const float* leaves, int B, int n_leaves, int n_pix, con
 int rhseg_concat_image_logits(const float* image, int c_image, const float* logits, int K, int B, int n_pix,
                               float* out, void* stream);
 
+/* Ternary targets as int8 ({1, 0, -1}; Data/dataset.py:227-265 only ever produces these three values) -> the fp32
+ * tensor the path reads: out[i] = (float) in[i], n elements, both pointers 16-byte aligned.  Lets a caller ship the
+ * wide target tensor over PCIe at a quarter of its fp32 size (FusedHierStep accepts int8 targets).                 */
+int rhseg_targets_i8_to_f32(const signed char* in, long n, float* out, void* stream);
+
 /* Data-parallel exchange buffer (no reference counterpart: train.py:201-241 is single-process; the
  * batch shards over ranks and ONE all-reduce of a packed fp64 buffer carries the step summary and
  * the head / FiLM parameter gradients).

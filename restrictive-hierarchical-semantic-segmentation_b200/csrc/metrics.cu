@@ -585,6 +585,38 @@ concat_planes_kernel(const float* __restrict__ a, int ca, const float* __restric
     st_stream<VEC>(dst + px, ld_stream<VEC>(src + px));
 }
 
+// ------------------------------------------------------------------------------------
+// Ternary targets shipped as int8 ({1, 0, -1}: what Data/dataset.py:227-265 produces, a quarter of the fp32 bytes over
+// PCIe) -> the fp32 tensor every kernel of the path reads.  16 values per thread: one 16-byte load, four 16-byte stores.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) widen_i8_kernel(const signed char* __restrict__ in, long n, float* __restrict__ out) {
+  pdl_wait();
+  const long n16 = n / 16;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n16; i += (long)gridDim.x * 256) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(in) + i);
+    const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 o;
+      o.x = (float)(signed char)(w[q] & 0xff);
+      o.y = (float)(signed char)((w[q] >> 8) & 0xff);
+      o.z = (float)(signed char)((w[q] >> 16) & 0xff);
+      o.w = (float)(signed char)((w[q] >> 24) & 0xff);
+      reinterpret_cast<float4*>(out)[i * 4 + q] = o;
+    }
+  }
+  for (long i = n16 * 16 + (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) out[i] = (float)in[i];
+}
+
+extern "C" int rhseg_targets_i8_to_f32(const signed char* in, long n, float* out, void* stream) {
+  if (!in || !out || n <= 0) return RHSEG_ERR_ARG;
+  if (!aligned16(in) || !aligned16(out)) return RHSEG_ERR_ARG;
+  const unsigned grid = (unsigned)std::min<long>((n / 16 + 255) / 256 + 1, 8L * device_sm_count());
+  launch_pdl(widen_i8_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, in, n, out);
+  RHSEG_LAUNCH_CHECK();
+  return RHSEG_OK;
+}
+
 extern "C" int rhseg_concat_image_logits(const float* image, int c_image, const float* logits, int K, int B, int n_pix,
                                          float* out, void* stream) {
   if (!image || !logits || !out || B <= 0 || c_image < 1 || K < 1 || n_pix <= 0) return RHSEG_ERR_ARG;

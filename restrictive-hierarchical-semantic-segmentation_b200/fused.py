@@ -27,6 +27,18 @@ from .tree_tables import ClassTree
 _I32 = ctypes.c_int32
 
 
+def widen_targets(target: torch.Tensor) -> torch.Tensor:
+    """fp32 view of the wide ternary target tensor.  int8 targets (the dataset's {1, 0, -1}; a quarter of the bytes over
+    PCIe) are widened by one kernel (rhseg_targets_i8_to_f32); other dtypes go through torch."""
+    if target.dtype == torch.float32:
+        return target
+    if target.dtype == torch.int8 and target.is_contiguous() and target.data_ptr() % 16 == 0:
+        out = torch.empty(target.shape, dtype=torch.float32, device=target.device)
+        call("rhseg_targets_i8_to_f32", ptr(target), target.numel(), ptr(out), stream_of(target))
+        return out
+    return target.float()
+
+
 class StepOutput:
     """Everything one training step reports, still on the device (no host sync)."""
     __slots__ = ("loss", "scalars", "level_ce", "level_dice", "consistency", "confusion", "ratios", "probs", "logits",
@@ -62,8 +74,7 @@ class _FusedStepFn(torch.autograd.Function):
         n = tree.num_levels
         n_active = n if level_cap is None else max(1, min(n, int(level_cap) + 1))  # train.py:121-126
         native.require_cuda(target)
-        if target.dtype != torch.float32:
-            target = target.float()
+        target = widen_targets(target)
         if target.dim() != 4 or target.shape[1] != sum(tree.head_channels):
             raise native.NativeError("target must be [B, sum(K_L), H, W] with sum(K_L) = %d, got %s"
                                      % (sum(tree.head_channels), tuple(target.shape)))
@@ -277,7 +288,7 @@ class _FusedFlatFn(torch.autograd.Function):
         if logits.dtype != torch.float32:
             raise native.NativeError("flat step expects float32 logits, got %s" % logits.dtype)
         z = logits if logits.is_contiguous() else logits.contiguous()
-        t = target if target.dtype == torch.float32 else target.float()
+        t = widen_targets(target)
         if not (t.stride(3) == 1 and t.stride(2) == t.shape[3]):
             t = t.contiguous()
         B, K, H, W = z.shape

@@ -58,6 +58,7 @@ SIGNATURES = {
     "rhseg_step_finalize": [_P, _P, _I, _I, _P, _P, _D, _L, _U, _P, _P, _P, _P],
     "rhseg_dp_grad_scales": [_P, _P, _I, _I, _P, _P, _P],
     "rhseg_level_eval": [_P, _P, _L, _L, _P, _L, _L, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
+    "rhseg_targets_i8_to_f32": [_P, _L, _P, _P],
     "rhseg_concat_image_logits": [_P, _I, _P, _I, _I, _I, _P, _P],
     "rhseg_stitch_levels": [_P, _I, _I, _I, _P, _I, _P, _P],
     "rhseg_confusion_from_logits": [_P, _P, _L, _L, _I, _I, _I, _I, _P, _P],

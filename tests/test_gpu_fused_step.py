@@ -192,3 +192,34 @@ def test_fused_step_replays_from_a_cuda_graph():
             assert torch.equal(a, b)
         for i, (a, b) in enumerate(zip(got[2], e_grads)):
             close(a, b, rtol=1e-6, what="graph grad %d/%d" % (it, i))  # same kernels: only the order of fp64 atomics differs
+
+
+@pytest.mark.parametrize("name", ["unet_tl_odd_notooth", "hrnet_ext"])
+def test_int8_targets_give_identical_results(name):
+    """The ternary targets may arrive as int8 (a quarter of the bytes over PCIe): rhseg_targets_i8_to_f32 widens them on
+    the device and the step's results are bit-identical to the fp32-target step."""
+    import rhseg_b200
+    fx = Fixture(name)
+    step = rhseg_b200.FusedHierStep(fx.tree, fx.level_weights)
+    mk = lambda ts: [t.to(DEV).requires_grad_(True) for t in ts]
+    target = torch.cat(fx.per_level("target"), dim=1).to(DEV)
+    outs = []
+    for tg in (target, target.to(torch.int8)):
+        feats = mk(fx.per_level("feats"))
+        hw, hb = mk(fx.per_level("head_w")), mk(fx.per_level("head_b"))
+        fw, fb = mk(fx.per_level("film_w", n=fx.nL - 1)), mk(fx.per_level("film_b", n=fx.nL - 1))
+        out = step(feats, hw, hb, fw, fb, tg, fx.out_size)
+        out.loss.backward()
+        outs.append((out, feats, hw))
+    a, b = outs
+    assert torch.equal(a[0].scalars, b[0].scalars)
+    for L in range(fx.nL):
+        assert torch.equal(a[0].confusion[L], b[0].confusion[L])
+        assert torch.equal(a[1][L].grad, b[1][L].grad)
+    # odd element counts and the 16-element main loop
+    from rhseg_b200 import native
+    for n in (1, 15, 16, 17, 4099):
+        src = torch.randint(-1, 2, (n + 16,), dtype=torch.int8, device=DEV)[:n]
+        dst = torch.empty(n, dtype=torch.float32, device=DEV)
+        native.call("rhseg_targets_i8_to_f32", src.data_ptr(), n, dst.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert torch.equal(dst, src.float())
