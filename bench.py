@@ -415,8 +415,9 @@ def dp_check(args, rank, world, dev):
     """N > 1, once before timing: the batch-sharded step (one shard per rank, summary exchange between forward and
     backward, gradient exchange after) against the SAME global batch run as one single-process step on rank 0.
     Rank 1's first sample has no tooth (its deeper-level Dice is NaN: the valid-sample counts differ between ranks).
-    Losses within 1e-5 relative, confusion matrices equal, gradients within 1e-5 (relative to the tensor's largest
-    entry) or the run fails."""
+    Losses within 1e-5 relative, gradients within 1e-5 (relative to the tensor's largest entry), the exchanged confusion
+    matrices equal to the exact integer sum of the ranks' matrices, and at most 1e-5 of the pixels moved against the
+    single-process matrices (argmax near-ties, see below) -- or the run fails."""
     import rhseg_b200
     from rhseg_b200 import dist as rdist
     name = args.workload
@@ -479,7 +480,17 @@ def dp_check(args, rank, world, dev):
     rflat = [p for grp in rp for p in grp]
     rg = torch.autograd.grad(ro.loss, rf + rflat)
     loss_rel = abs(glob["total"].item() - ro.loss.item()) / max(abs(ro.loss.item()), 1e-30)
-    conf_eq = all(torch.equal(a, b) for a, b in zip(glob["confusion"], ro.confusion))
+    # integers: (1) the exchanged confusion matrices must equal the exact int64 sum over ranks of the local ones;
+    # (2) against the single-process step a handful of pixels may move: its conv kernel splits the pixel tiles between
+    # CTAs at other places (the split depends on the batch), logits differ in the last bit and exact near-ties of the
+    # argmax flip -- reported as moved pixels, bounded at 1e-5 of the evaluated pixels
+    conf_eq, moved = True, 0
+    for L, (a, b) in enumerate(zip(glob["confusion"], ro.confusion)):
+        local = out.confusion[L].clone()
+        torch.distributed.all_reduce(local)
+        conf_eq = conf_eq and torch.equal(a, local)
+        moved += int((a - b).abs().sum().item()) // 2
+    px_eval = Bg * wl["H"] * wl["W"] * len(chans)
     grad_rel, off = 0.0, 0
     for p, want in zip(flat_params, rg[len(rf):]):  # DDP mean over ranks of the parameter gradients
         got = (red[off:off + p.numel()] / world).view(want.shape)
@@ -488,19 +499,21 @@ def dp_check(args, rank, world, dev):
     for L in range(len(feats)):  # what the donor's DDP sees: local dfeats / world == the global step's dfeats of this shard
         want = rg[L][sl]
         grad_rel = max(grad_rel, ((grads[L] / world - want).abs().max() / want.abs().max().clamp_min(1e-30)).item())
-    agg = torch.tensor([loss_rel, grad_rel, 0.0 if conf_eq else 1.0, float(xs)], dtype=torch.float64, device=dev)
+    agg = torch.tensor([loss_rel, grad_rel, 0.0 if conf_eq else 1.0, float(xs), float(moved)], dtype=torch.float64, device=dev)
     torch.distributed.all_reduce(agg, op=torch.distributed.ReduceOp.MAX)
     if px is not None:
         px.close()
     n_valid = [int(glob["n_dice"][L].item()) for L in range(len(chans))]
     res = {"loss_rel": agg[0].item(), "confusion_equal": agg[2].item() == 0.0, "grad_rel": agg[1].item(),
-           "xchg_status": int(agg[3].item()), "global_batch": Bg, "dice_valid_samples_per_level": n_valid,
+           "xchg_status": int(agg[3].item()), "argmax_near_tie_pixels_moved_vs_single_process": int(agg[4].item()),
+           "pixels_evaluated": px_eval, "global_batch": Bg, "dice_valid_samples_per_level": n_valid,
            "exchange": "p2p" if px is not None else "nccl",
            "what": "sharded (world=%d, %d samples per rank, rank 1 holds a sample without tooth) vs the same global batch in one process"
                    % (world, Bl)}
     del data, h, feats, params, rf, rp, rg, grads
     torch.cuda.empty_cache()
-    if not (res["loss_rel"] <= 1e-5 and res["grad_rel"] <= 1e-5 and res["confusion_equal"] and res["xchg_status"] == 0):
+    if not (res["loss_rel"] <= 1e-5 and res["grad_rel"] <= 1e-5 and res["confusion_equal"] and res["xchg_status"] == 0
+            and res["argmax_near_tie_pixels_moved_vs_single_process"] <= 1e-5 * px_eval):
         raise SystemExit("data-parallel check failed: %s" % json.dumps(res))
     return res
 
