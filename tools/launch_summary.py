@@ -5,7 +5,7 @@ import re
 import sys
 
 
-def main(path, per_step_marker="film_fold", per_step_count=2):
+def main(path, per_step_marker="step_finalize", per_step_count=1):
     rows = []
     lines = [l for l in open(path) if not l.startswith("==")]
     for r in csv.DictReader(lines):
