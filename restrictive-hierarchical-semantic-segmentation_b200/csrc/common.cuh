@@ -1,6 +1,8 @@
 // Shared device helpers for the rhseg_b200 kernels (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <mutex>
+#include <vector>
 #include <stdint.h>
 #include <cstdlib>
 #pragma GCC visibility push(default)
@@ -73,14 +75,47 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 
 // SM count of the current device (cached per process; grids are sized from it)
-inline int device_sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    cached = n > 0 ? n : 148;
+inline int device_sm_count() {  // of the CURRENT device (a process may drive several)
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
   }
-  return cached;
+  return cached[dev];
+}
+
+// Launch preparation of the persistent kernels, cached: raising the dynamic shared-memory limit and asking for the
+// resident CTAs per SM are driver calls of several microseconds each -- noticeable on the eager drop-in route, which is
+// bound by host time per launch.  Keyed by (device, kernel, threads, shared memory); the limit only ever grows.
+inline cudaError_t cached_launch_prep(const void* kern, int threads, size_t smem, size_t smem_limit, int* per_sm) {
+  struct Entry { int dev; const void* f; int threads; size_t smem; int per_sm; };
+  struct Limit { int dev; const void* f; size_t limit; };
+  static std::mutex mu;
+  static std::vector<Entry> occ;
+  static std::vector<Limit> lim;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  Limit* l = nullptr;
+  for (auto& x : lim)
+    if (x.dev == dev && x.f == kern) { l = &x; break; }
+  if (l == nullptr || l->limit < smem_limit) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    if (e != cudaSuccess) return e;
+    if (l) l->limit = smem_limit; else lim.push_back(Limit{dev, kern, smem_limit});
+  }
+  for (const auto& x : occ)
+    if (x.dev == dev && x.f == kern && x.threads == threads && x.smem == smem) { *per_sm = x.per_sm; return cudaSuccess; }
+  int n = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
+  if (e != cudaSuccess) return e;
+  occ.push_back(Entry{dev, kern, threads, smem, n});
+  *per_sm = n;
+  return cudaSuccess;
 }
 
 // Persistent grid for `units` equal work items and `slots` resident CTAs: the smallest grid that keeps the

@@ -475,9 +475,8 @@ static int launch_conv_bwd(const float* feats, const float* dz, const float* eff
   constexpr int T = CFG::CONSUMERS * J * VEC;
   const size_t smem = 128 + ((size_t)CFG::NS * CFG::CH * (T + 4) + (size_t)CFG::NCW * CFG::CH * KP) * sizeof(float);
   auto kern = conv_bwd_kernel<K, VEC, J, CFG>;
-  RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CFG::THREADS, smem));
+  RHSEG_CUDA(cached_launch_prep(reinterpret_cast<const void*>(kern), CFG::THREADS, smem, smem, &per_sm));
   if (per_sm < 1) return RHSEG_ERR_UNSUPPORTED;
   const int n_tiles = (N + T - 1) / T;
   const int n_stages = (C + CFG::CH - 1) / CFG::CH;

@@ -347,9 +347,8 @@ static int launch_fwd(const float* feats, const float* eff_w, const float* eff_b
   constexpr int T = CFG::CONSUMERS * J * VEC;
   const size_t smem = 128 + ((size_t)CFG::NS * CFG::CH * (T + 4) + (size_t)C * KP + CFG::NCW * K) * sizeof(float);
   auto kern = head_fwd_kernel<K, VEC, J, MODE, CFG>;
-  RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CFG::THREADS, smem));
+  RHSEG_CUDA(cached_launch_prep(reinterpret_cast<const void*>(kern), CFG::THREADS, smem, smem, &per_sm));
   if (per_sm < 1) return RHSEG_ERR_UNSUPPORTED;
   const int n_tiles = (N + T - 1) / T;
   const int n_stages = (C + CFG::CH - 1) / CFG::CH;

@@ -437,8 +437,7 @@ static int launch_band(const float* z_lo, const float* prev_probs, const int32_t
   int per_sm = 0;
   const size_t smem0 = smem_for(8);
   if (smem0 > 200 * 1024) return RHSEG_OK;
-  RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(smem_for(H), 200 * 1024)));
-  RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ncons + 32, smem0));
+  RHSEG_CUDA(cached_launch_prep(reinterpret_cast<const void*>(kern), ncons + 32, smem0, std::min<size_t>(smem_for(H), 200 * 1024), &per_sm));
   if (per_sm < 1) return RHSEG_OK;
   static int tune_ctas = -1;
   if (tune_ctas < 0) { const char* e = getenv("RHSEG_TUNE_UP_CTAS"); tune_ctas = e ? atoi(e) : 0; }

@@ -351,9 +351,8 @@ static int launch_eval_pipe(const float* logits, const float* targets, long t_bs
   if (tune < 0) { const char* e = getenv("RHSEG_TUNE_EVAL"); tune = e ? atoi(e) : 0; }
   const int ns = tune == 1 ? 3 : (tune == 2 ? 4 : 2);
   const size_t smem = 128 + (size_t)ns * STAGE;
-  RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EVP_THREADS, smem));
+  RHSEG_CUDA(cached_launch_prep(reinterpret_cast<const void*>(kern), EVP_THREADS, smem, smem, &per_sm));
   if (per_sm < 1) return RHSEG_ERR_UNSUPPORTED;
   const long units = (long)B * N / 16;
   // every CTA gets at least two full stages of work; one resident wave at most

@@ -533,9 +533,8 @@ static int launch_dz_band(const float* dz_hi, const FusedDzArgs& fa, int B, int 
   if (Wf > ncons) return RHSEG_OK;  // one low-res column per consumer thread in the x adjoint
   const size_t smem = fixed + (size_t)ns * stage;
   if (smem > 200 * 1024) return RHSEG_OK;
-  RHSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  RHSEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ncons + 32, smem));
+  RHSEG_CUDA(cached_launch_prep(reinterpret_cast<const void*>(kern), ncons + 32, smem, smem, &per_sm));
   if (per_sm < 1) return RHSEG_OK;
   static int tune_ctas = -1;
   if (tune_ctas < 0) { const char* e = getenv("RHSEG_TUNE_DZ_CTAS"); tune_ctas = e ? atoi(e) : 0; }

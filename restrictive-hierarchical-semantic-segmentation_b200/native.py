@@ -112,7 +112,14 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_of(t):
+    """Raw cudaStream_t of the current stream on the tensor's device (the raw accessor avoids building a Stream object:
+    ~9 us -> < 1 us per call on the eager drop-in route, which is bound by host time)."""
+    if _raw_stream is not None and t.device.index is not None:
+        return _raw_stream(t.device.index)
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
