@@ -309,5 +309,6 @@ def hier_head_forward(tree: ClassTree, feats: Sequence[torch.Tensor],
     n = tree.num_levels
     if not (len(feats) == len(head_w) == len(head_b) == n and len(film_w) == len(film_b) == n - 1):
         raise native.NativeError("hier_head_forward: expected %d levels of features/heads and %d FiLMs" % (n, n - 1))
-    outs = _HierHeadFn.apply(tree, out_size, *feats, *head_w, *head_b, *film_w, *film_b)
+    with native.device_guard(feats[0]):
+        outs = _HierHeadFn.apply(tree, out_size, *feats, *head_w, *head_b, *film_w, *film_b)
     return list(outs[:n]), list(outs[n:])

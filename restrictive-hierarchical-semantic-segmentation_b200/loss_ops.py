@@ -46,8 +46,9 @@ def _plane_contiguous(t: torch.Tensor) -> torch.Tensor:
 
 class _LevelLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, outs, targets, weights, smooth, logits_input):
+    def forward(ctx, outs, targets, weights, smooth, logits_input, token):
         native.require_cuda(outs, targets, weights)
+        ctx.token = token
         if outs.dtype != torch.float32:
             raise native.NativeError("losses expect float32 predictions, got %s" % outs.dtype)
         outs = outs if outs.is_contiguous() else outs.contiguous()
@@ -74,8 +75,9 @@ class _LevelLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_ce, g_dice, _g_counts, _g_stats):
         outs, targets, coef = ctx.saved_tensors
+        ctx.token[0] = False  # this node has run backward: a memoised result must not be handed out again (its graph is freed)
         if g_ce is None and g_dice is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         B, K = outs.shape[0], outs.shape[1]
         n_pix = outs[0, 0].numel()
 
@@ -89,7 +91,7 @@ class _LevelLossFn(torch.autograd.Function):
         dz = torch.empty_like(outs)
         call("rhseg_loss_bwd", ptr(outs), ptr(targets), targets.stride(0), targets.stride(1), ptr(coef),
              ptr(g_ce), ptr(g_dice), B, K, n_pix, 1 if ctx.logits_input else 0, ptr(dz), stream_of(outs))
-        return dz, None, None, None, None
+        return dz, None, None, None, None, None
 
 
 class LevelLoss:
@@ -107,7 +109,8 @@ class LevelLoss:
         return self.dice if float(self.counts[0].item()) > 0 else None
 
 
-# (outs_ref, outs_version, targets_ref, targets_version, key, result).  Results carry autograd
+# (outs_ref, outs_version, targets_ref, targets_version, key, result, token).  token[0] turns False once the node has run
+# backward (a second consumer then gets a fresh node instead of a freed graph).  Results carry autograd
 # history, so the memo is kept tiny: the reference calls CE then Dice on the same tensors
 # back to back (train.py:136-137) and one or two live entries cover that.
 _MEMO = []
@@ -126,9 +129,9 @@ def level_loss(outs, targets, class_weight, smooth: Optional[float], logits_inpu
     grad = torch.is_grad_enabled() and outs.requires_grad
     wkey = tuple(float(w) for w in class_weight) if class_weight is not None else None
     for i in range(len(_MEMO) - 1, -1, -1):
-        o_ref, o_ver, t_ref, t_ver, key, res = _MEMO[i]
+        o_ref, o_ver, t_ref, t_ver, key, res, token = _MEMO[i]
         o, t = o_ref(), t_ref()
-        if o is None or t is None:
+        if o is None or t is None or not token[0]:
             del _MEMO[i]
             continue
         if o is outs and t is targets and o_ver == outs._version and t_ver == targets._version \
@@ -137,10 +140,12 @@ def level_loss(outs, targets, class_weight, smooth: Optional[float], logits_inpu
             return res
     w = weight_tensor(class_weight, outs.device)
     sm = 0.0 if smooth is None else float(smooth)
-    ce, dice, counts, stats = _LevelLossFn.apply(outs, targets, w, sm, bool(logits_input))
+    token = [True]
+    with native.device_guard(outs):
+        ce, dice, counts, stats = _LevelLossFn.apply(outs, targets, w, sm, bool(logits_input), token)
     res = LevelLoss(ce, dice, counts, stats)
     _MEMO.append((weakref.ref(outs), outs._version, weakref.ref(targets), targets._version,
-                  (wkey, bool(logits_input), grad, sm), res))
+                  (wkey, bool(logits_input), grad, sm), res, token))
     if len(_MEMO) > _MEMO_MAX:
         del _MEMO[0]
     return res
@@ -191,7 +196,8 @@ def consistency_loss(probs_per_level, levels, parent_of, reduction="mean"):
         if G == 0:
             continue
         cur, prev = probs_per_level[L], probs_per_level[L - 1]
-        sums = _ConsistencyFn.apply(cur.float(), prev.float(), tables[L], G)
+        with native.device_guard(cur):
+            sums = _ConsistencyFn.apply(cur.float(), prev.float(), tables[L], G)
         if reduction == "mean":
             sums = sums / float(prev.shape[0] * prev[0, 0].numel())
         part = sums.sum()

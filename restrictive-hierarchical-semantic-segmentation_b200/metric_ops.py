@@ -30,8 +30,9 @@ def confusion_matrix(probs, targets, child_classes: bool) -> torch.Tensor:
         raise native.NativeError("prediction / target shape mismatch: %s vs %s" % (tuple(p.shape), tuple(t.shape)))
     nc = K + 1 if child_classes else K
     conf = torch.empty((nc, nc), dtype=torch.int64, device=p.device)
-    call("rhseg_confusion_matrix", ptr(p), p.stride(0), p.stride(1), ptr(t), t.stride(0), t.stride(1),
-         B, K, n_pix, 1 if child_classes else 0, ptr(conf), stream_of(p))
+    with native.device_guard(p):
+        call("rhseg_confusion_matrix", ptr(p), p.stride(0), p.stride(1), ptr(t), t.stride(0), t.stride(1),
+             B, K, n_pix, 1 if child_classes else 0, ptr(conf), stream_of(p))
     return conf
 
 
@@ -45,8 +46,9 @@ def confusion_from_logits(logits, targets, child_classes: bool) -> torch.Tensor:
     n_pix = z.shape[2] * z.shape[3]
     nc = K + 1 if child_classes else K
     conf = torch.empty((nc, nc), dtype=torch.int64, device=z.device)
-    call("rhseg_confusion_from_logits", ptr(z), ptr(t), t.stride(0), t.stride(1), B, K, n_pix,
-         1 if child_classes else 0, ptr(conf), stream_of(z))
+    with native.device_guard(z):
+        call("rhseg_confusion_from_logits", ptr(z), ptr(t), t.stride(0), t.stride(1), B, K, n_pix,
+             1 if child_classes else 0, ptr(conf), stream_of(z))
     return conf
 
 
@@ -54,7 +56,8 @@ def ratios(conf: torch.Tensor) -> torch.Tensor:
     """fp32 [5,nc]: rows dice/F1, IoU, accuracy(=recall), precision, recall."""
     nc = conf.shape[0]
     out = torch.empty((5, nc), dtype=torch.float32, device=conf.device)
-    call("rhseg_metric_ratios", ptr(conf), nc, ptr(out), stream_of(conf))
+    with native.device_guard(conf):
+        call("rhseg_metric_ratios", ptr(conf), nc, ptr(out), stream_of(conf))
     return out
 
 
@@ -68,8 +71,9 @@ def predict_onehot(logits, targets, want_index=False):
     onehot = torch.empty_like(z)
     eval_t = torch.empty_like(z)
     idx = torch.empty((B,) + tuple(z.shape[2:]), dtype=torch.int32, device=z.device) if want_index else None
-    call("rhseg_predict_onehot", ptr(z), ptr(t), t.stride(0), t.stride(1), B, K, n_pix, ptr(onehot), ptr(eval_t),
-         ptr(idx), stream_of(z))
+    with native.device_guard(z):
+        call("rhseg_predict_onehot", ptr(z), ptr(t), t.stride(0), t.stride(1), B, K, n_pix, ptr(onehot), ptr(eval_t),
+             ptr(idx), stream_of(z))
     return (onehot, eval_t, idx) if want_index else (onehot, eval_t)
 
 

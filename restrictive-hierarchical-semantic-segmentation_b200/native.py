@@ -123,6 +123,26 @@ def stream_of(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(t):
+    """Context manager that makes the tensor's device current while kernels are launched for it (they launch on the
+    device's current stream and size their grids for the current device).  Free when it already is."""
+    idx = t.device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(idx)
+
+
 def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:

@@ -354,3 +354,30 @@ def test_eval_mode_backbone_reuse_is_output_identical():
     sum(z.sum() for z in z3).backward()
     assert m.heads[0].conv.weight.grad is not None and m.films[0].mlp[1].weight.grad is not None
     assert m.inc0.conv.conv[0].weight.grad is not None
+
+
+def test_one_backward_per_loss_term_on_the_same_tensors():
+    """CE back-propagated on its own, then Dice requested for the same (logits, targets) objects.  The memoised
+    node has run backward by then (its graph is freed): the second module call must get a fresh node, as the reference's
+    two independent modules do, and the accumulated gradient equals d(CE + Dice)."""
+    import os
+    import numpy as np
+    from helpers import GOLDEN
+    from rhseg_b200.Metrics import losses
+    z = np.load(os.path.join(GOLDEN, "flat7.npz"))
+    logits = torch.from_numpy(z["logits"]).to(DEV).requires_grad_(True)
+    t = torch.from_numpy(z["target"]).float().to(DEV)
+    w = [float(v) for v in z["weights"]]
+    losses.CrossEntropyLoss()(logits, t, class_weight=w, logits_input=True).backward()
+    di = losses.SoftDiceLoss(num_classes=7)(logits, t, class_weight=w, logits_input=True)
+    di.backward()
+    close(logits.grad, z["dlogits"], what="dlogits after two separate backward passes")
+    # the usual sequence (both terms, one backward) still shares one node
+    import rhseg_b200
+    rhseg_b200.clear_memo()
+    logits.grad = None
+    ce = losses.CrossEntropyLoss()(logits, t, class_weight=w, logits_input=True)
+    di = losses.SoftDiceLoss(num_classes=7)(logits, t, class_weight=w, logits_input=True)
+    assert ce.grad_fn is di.grad_fn
+    (ce + di).backward()
+    close(logits.grad, z["dlogits"], what="dlogits, shared node")
