@@ -496,8 +496,12 @@ static int fwd_upsampled(const float* z_lo, const float* prev_probs, const int32
         if (evalk == 0) RHSEG_BAND_V(0, K); else RHSEG_BAND_V(1, K);
       } else {
         const bool single = hint == K;
+        bool uniform2 = false;
+        if constexpr (K == 4) uniform2 = hint == 2;  // two parents with two children each (extended tree, level 2)
         if (single) {
           if (evalk == 0) RHSEG_BAND_V(0, K); else if (evalk == 1) RHSEG_BAND_V(1, K); else RHSEG_BAND_V(2, K);
+        } else if (uniform2) {
+          if constexpr (K == 4) { if (evalk == 0) RHSEG_BAND_V(0, 2); else if (evalk == 1) RHSEG_BAND_V(1, 2); else RHSEG_BAND_V(2, 2); }
         } else {
           if (evalk == 0) RHSEG_BAND_V(0, 0);
           else if constexpr (K <= 6) { if (evalk == 1) RHSEG_BAND_V(1, 0); else RHSEG_BAND_V(2, 0); }

@@ -517,6 +517,12 @@ extern "C" int rhseg_level_eval(const float* logits, const float* targets, long 
         if (cons_in) return launch_eval_pipe<KK, 2, KK>(logits, targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, table, B, N, stats, cons, conf, idx_out, st);
         return launch_eval_pipe<KK, 1, KK>(logits, targets, t_bstride, t_cstride, nullptr, 0, 0, nullptr, table, B, N, stats, cons, conf, idx_out, st);
       }
+      if constexpr (KK == 4) {
+        if (hint == 2) {  // two parents with two children each (extended tree, level 2): layout fixed at compile time
+          if (cons_in) return launch_eval_pipe<KK, 2, 2>(logits, targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, table, B, N, stats, cons, conf, idx_out, st);
+          return launch_eval_pipe<KK, 1, 2>(logits, targets, t_bstride, t_cstride, nullptr, 0, 0, nullptr, table, B, N, stats, cons, conf, idx_out, st);
+        }
+      }
       if (cons_in) {
         // table-driven group layout + consistency with K > 6 would spill in the pipelined kernel: generic kernel below
         if constexpr (KK <= 6) return launch_eval_pipe<KK, 2, 0>(logits, targets, t_bstride, t_cstride, parent_targets, pt_bstride, pt_cstride, prev_idx, table, B, N, stats, cons, conf, idx_out, st);

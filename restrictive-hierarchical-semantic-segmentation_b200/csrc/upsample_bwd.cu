@@ -672,7 +672,10 @@ static int launch_adjoint(const float* dz_hi, const FusedDzArgs& fa, int hint, i
       } else if constexpr (MODE == RHSEG_ACT_SIGMOID) {
         if (no_act) RHSEG_DZB_V(1, K); else if (unif) RHSEG_DZB_V(2, K); else RHSEG_DZB_V(0, K);
       } else {
+        bool uniform2 = false;
+        if constexpr (K == 4) uniform2 = hint == 2;  // two parents with two children each (class_tree_tl_extended.json, level 2)
         if (no_act) RHSEG_DZB_V(1, K); else if (hint == K) RHSEG_DZB_V(0, K);
+        else if (uniform2) { if constexpr (K == 4) RHSEG_DZB_V(0, 2); }
         else if constexpr (K <= 5) RHSEG_DZB_V(0, 0);  // table-driven group layout with K > 5 would spill: tiled kernel below
       }
 #undef RHSEG_DZB_V
