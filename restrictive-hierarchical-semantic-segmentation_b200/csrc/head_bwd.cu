@@ -201,13 +201,19 @@ __device__ __noinline__ void param_grads_tail(const ParamTail& pt, const double*
   }
 }
 
+// min-blocks 1 for the scalar-row K = 3 instance only (0 = unspecified): left alone, ptxas squeezes that instance to 96
+// registers (+ spills) for a second CTA per SM that the shared-memory ring rules out anyway -- 121 vs 112 us in the step.
 template <int K, int VEC, int J, typename CFG>
-__global__ void __launch_bounds__(CFG::THREADS)
+__global__ void __launch_bounds__(CFG::THREADS, ((VEC == 1 && K == 3) ? 1 : 0))
 conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, const float* __restrict__ eff_w,
                 int C, int N, int n_tiles, int n_stages, long units_total, int a0, int w_shared, float* __restrict__ dfeats,
                 double* __restrict__ S, double* __restrict__ s, ParamTail pt) {
   pdl_wait();
   constexpr int KP = pad_k(K);
+  // Register arrays and inner loops run over KC channels.  K = 3 computes on its zero-padded fourth channel (dz loads as
+  // 0, the weight table is zero-padded already): ptxas schedules the K = 3 instance at 96 registers with little load
+  // batching (111 us per HRNet launch against 96 us for K = 4 and K = 2); with four channels it IS the K = 4 schedule.
+  constexpr int KC = (K == 3) ? 4 : K;
   constexpr int P = J * VEC;
   constexpr int NCONS = CFG::CONSUMERS;
   constexpr int T = NCONS * P;
@@ -293,7 +299,7 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
     tiles_since_flush = 0;
   };
 
-  float g_next[K][P];
+  float g_next[KC][P];
   auto load_dz = [&](int bb, int tt) {
     const int q0 = tt * T;
     const int q_act = min(T, N - q0);
@@ -301,9 +307,9 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
     for (int j = 0; j < J; ++j) {
       const int l = (j * NCONS + tid) * VEC;
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
+      for (int k = 0; k < KC; ++k) {
         Vec<VEC> t;
-        if (l < q_act) t = ld_cached<VEC>(dz + ((size_t)bb * K + k) * N + q0 + l);
+        if (k < K && l < q_act) t = ld_cached<VEC>(dz + ((size_t)bb * K + k) * N + q0 + l);
         else {
 #pragma unroll
           for (int v = 0; v < VEC; ++v) t.v[v] = 0.f;
@@ -340,13 +346,13 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
     // that its L2 latency hides behind this unit's barrier wait and math
     int lp[J];
     bool ok[J];
-    float g[K][P];
+    float g[KC][P];
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       lp[j] = (j * NCONS + tid) * VEC;
       ok[j] = lp[j] < t_act;
 #pragma unroll
-      for (int k = 0; k < K; ++k)
+      for (int k = 0; k < KC; ++k)
 #pragma unroll
         for (int v = 0; v < VEC; ++v) g[k][j * VEC + v] = g_next[k][j * VEC + v];
     }
@@ -397,7 +403,7 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
           f[0] = row[offv + j * NCONS];
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k)
+        for (int k = 0; k < KC; ++k)
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
             // NaN-safe masking: stale shared memory past the tile end may hold any bit pattern
@@ -410,7 +416,7 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
           for (int v = 0; v < VEC; ++v) {
             float a = 0.f;
 #pragma unroll
-            for (int k = 0; k < K; ++k) a = fmaf(w[k], g[k][j * VEC + v], a);
+            for (int k = 0; k < KC; ++k) a = fmaf(w[k], g[k][j * VEC + v], a);
             o.v[v] = a;
           }
           st_stream<VEC>(dfb + (size_t)cc * N + lp[j], o);
