@@ -139,7 +139,7 @@ def synth_inputs(wl, B, seed, device="cpu", pin=False, notooth_sample=None):
     tl = synth.synth_targets(levels, groups, B, wl["H"], wl["W"], g, device=dev)
     if notooth_sample is not None and len(levels) > 1 and groups[0]:
         tl = synth.drop_class_in_sample(tl, levels, groups, notooth_sample, groups[0][0][0])
-    host["target"] = torch.cat(tl, dim=1)
+    host["target"] = torch.cat(tl, dim=1).contiguous()  # NCHW like the dataset's tensors (cat of one permuted one-hot keeps its layout)
     del tl
     weights = wl["weights"] or [[1.0] * k for k in chans]
     if pin:
