@@ -218,79 +218,165 @@ __device__ __forceinline__ SampleLoss sample_loss(const double* __restrict__ st,
   return r;
 }
 
-// All levels in parallel: thread <-> (level, sample); shared-memory fp64 atomics per level.
+// All levels of a step in one launch, ONE barrier.  The kernel sits on the critical path between the last forward kernel
+// and the first gradient kernel and is pure latency, so it is laid out to have a single dependent chain:
+//   every thread derives the workspace offsets it needs itself (<= 8 integer steps, no shared table, no barrier);
+//   thread <-> (level, sample): per-sample CE / Dice + backward coefficients kept in registers, its four sums into a
+//     shared slot; concurrently thread <-> (level, class): the five ratio vectors; thread <-> (level, group): consistency;
+//   barrier;
+//   the (level, sample) threads read their level's valid count from the slots, scale the Dice coefficients and write the
+//     coefficients ONCE (no read-modify-write pass); thread L < n_levels forms level L's outputs (fixed summation order),
+//     thread 0 the totals.
+constexpr int SF_MAX_SLOTS = 256;  // (level, sample) pairs handled by the fast layout (else: strided passes below)
+
+struct StepOffsets { size_t w, k, c, r; };
+__device__ __forceinline__ StepOffsets step_offsets(const StepLevels& lv, int B, int L) {
+  StepOffsets o{0, 0, 0, 2 + 4 * (size_t)lv.n_levels};
+  for (int i = 0; i < L; ++i) {
+    const int K = lv.K[i], nc = lv.child[i] ? K + 1 : K;
+    o.w += (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K + (size_t)nc * nc;
+    o.k += K;
+    o.c += (size_t)B * K * 3;
+    o.r += 5 * (size_t)nc;
+  }
+  return o;
+}
+
 __global__ void __launch_bounds__(256)
 step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ weights, StepLevels lv, int B,
                      double smooth, double inv_bn, unsigned level_mask, float* __restrict__ out, float* __restrict__ coef,
                      double* __restrict__ summary) {
   pdl_wait();
-  __shared__ double acc[RHSEG_MAX_LEVELS][4];  // ce_sum, dice_sum, n_dice, n_ce
-  __shared__ size_t w_off[RHSEG_MAX_LEVELS + 1], k_off[RHSEG_MAX_LEVELS + 1], c_off[RHSEG_MAX_LEVELS + 1], r_off[RHSEG_MAX_LEVELS + 1];
+  __shared__ double slot[SF_MAX_SLOTS][4];  // per (level, sample): ce, dice (0 if dropped), dice_ok, ce_ok
+  __shared__ double cons_part[RHSEG_MAX_LEVELS][RHSEG_MAX_K];  // per (level, group); entries g < G[L] are written below
   const int tid = threadIdx.x, nL = lv.n_levels;
-  if (tid == 0) {
-    w_off[0] = k_off[0] = c_off[0] = 0;
-    r_off[0] = 2 + 4 * (size_t)nL;
-    for (int L = 0; L < nL; ++L) {
-      const int K = lv.K[L], nc = lv.child[L] ? K + 1 : K;
-      w_off[L + 1] = w_off[L] + (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K + (size_t)nc * nc;
-      k_off[L + 1] = k_off[L] + K;
-      c_off[L + 1] = c_off[L] + (size_t)B * K * 3;
-      r_off[L + 1] = r_off[L] + 5 * (size_t)nc;
+  const int n_pairs = nL * B;
+  // (1) per-sample losses: thread <-> (level, sample); more than SF_MAX_SLOTS pairs are handled in strided rounds
+  for (int base = 0; base < n_pairs; base += SF_MAX_SLOTS) {
+    const int e = base + tid;
+    const bool live = e < n_pairs && tid < SF_MAX_SLOTS;
+    float cf[RHSEG_KERNEL_MAX_K * 3];
+    int L = 0, b = 0, K = 1;
+    StepOffsets o{0, 0, 0, 0};
+    SampleLoss r{0.0, 0.0, false, false};
+    if (live) {
+      L = e / B; b = e - L * B; K = lv.K[L];
+      o = step_offsets(lv, B, L);
+      r = sample_loss(ws + o.w + (size_t)b * K * RHSEG_NSTAT, weights + o.k, K, B, smooth, cf);
+      slot[tid][0] = r.ce;
+      slot[tid][1] = r.dice_ok ? r.dice : 0.0;
+      slot[tid][2] = r.dice_ok ? 1.0 : 0.0;
+      slot[tid][3] = r.ce_nan ? 0.0 : 1.0;
     }
-  }
-  __shared__ double cons_sm[RHSEG_MAX_LEVELS];
-  if (tid < RHSEG_MAX_LEVELS * 4) (&acc[0][0])[tid] = 0.0;
-  if (tid < RHSEG_MAX_LEVELS) cons_sm[tid] = 0.0;
-  __syncthreads();
-  // (1) per-sample losses: thread <-> (level, sample)
-  for (int e = tid; e < nL * B; e += blockDim.x) {
-    const int L = e / B, b = e - L * B, K = lv.K[L];
-    const SampleLoss r = sample_loss(ws + w_off[L] + (size_t)b * K * RHSEG_NSTAT, weights + k_off[L], K, B, smooth,
-                                     coef + c_off[L] + (size_t)b * K * 3);
-    atomicAdd(&acc[L][0], r.ce);
-    if (r.dice_ok) { atomicAdd(&acc[L][1], r.dice); atomicAdd(&acc[L][2], 1.0); }
-    if (!r.ce_nan) atomicAdd(&acc[L][3], 1.0);
-  }
-  // (2) concurrently, from the top of the block: the five per-class ratios, thread <-> (level, class)
-  {
-    int e = (int)blockDim.x - 1 - tid, L = 0;
-    while (L < nL && e >= (lv.child[L] ? lv.K[L] + 1 : lv.K[L])) { e -= (lv.child[L] ? lv.K[L] + 1 : lv.K[L]); ++L; }
-    if (L < nL) {
-      const int K = lv.K[L], nc = lv.child[L] ? K + 1 : K, c = e;
-      const long long* conf = reinterpret_cast<const long long*>(ws + w_off[L] + (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K);
-      long long rowv[RHSEG_KERNEL_MAX_K + 1], colv[RHSEG_KERNEL_MAX_K + 1];
+    if (base == 0) {
+      // (2) concurrently, from the top of the block: the five per-class ratios, thread <-> (level, class)
+      int c = (int)blockDim.x - 1 - tid, Lr = 0;
+      while (Lr < nL && c >= (lv.child[Lr] ? lv.K[Lr] + 1 : lv.K[Lr])) { c -= (lv.child[Lr] ? lv.K[Lr] + 1 : lv.K[Lr]); ++Lr; }
+      if (Lr < nL) {
+        const int Kr = lv.K[Lr], nc = lv.child[Lr] ? Kr + 1 : Kr;
+        const StepOffsets orr = step_offsets(lv, B, Lr);
+        const long long* conf = reinterpret_cast<const long long*>(ws + orr.w + (size_t)B * Kr * RHSEG_NSTAT + RHSEG_MAX_K);
+        long long rowv[RHSEG_KERNEL_MAX_K + 1], colv[RHSEG_KERNEL_MAX_K + 1];
 #pragma unroll
-      for (int j = 0; j <= RHSEG_KERNEL_MAX_K; ++j) {
-        rowv[j] = j < nc ? conf[c * nc + j] : 0;
-        colv[j] = j < nc ? conf[j * nc + c] : 0;
+        for (int j = 0; j <= RHSEG_KERNEL_MAX_K; ++j) {
+          rowv[j] = j < nc ? conf[c * nc + j] : 0;
+          colv[j] = j < nc ? conf[j * nc + c] : 0;
+        }
+        long long tp = conf[c * nc + c], row = 0, col = 0;
+#pragma unroll
+        for (int j = 0; j <= RHSEG_KERNEL_MAX_K; ++j) { row += rowv[j]; col += colv[j]; }
+        const long long fp = col - tp, fn = row - tp;
+        auto safe = [](float num, float den) { return num / (den == 0.f ? 1.f : den); };
+        const float tpf = (float)tp, fpf = (float)fp, fnf = (float)fn;
+        float* orow = out + orr.r;
+        orow[0 * nc + c] = safe(2.0f * tpf, (2.0f * tpf + 1.0f * fnf) + fpf);
+        orow[1 * nc + c] = safe(tpf, (float)(col + row - tp));
+        orow[2 * nc + c] = safe(tpf, (float)(tp + fn));
+        orow[3 * nc + c] = safe(tpf, (float)(tp + fp));
+        orow[4 * nc + c] = safe(tpf, (float)(tp + fn));
       }
-      long long tp = conf[c * nc + c], row = 0, col = 0;
+      // (3) concurrently: consistency sums, thread <-> (level, group) in the middle of the block
+      if (tid >= 64 && tid < 64 + nL * RHSEG_MAX_K) {
+        const int Lc = (tid - 64) / RHSEG_MAX_K, g = (tid - 64) % RHSEG_MAX_K;
+        if (g < lv.G[Lc]) {
+          const StepOffsets oc = step_offsets(lv, B, Lc);
+          cons_part[Lc][g] = (ws + oc.w + (size_t)B * lv.K[Lc] * RHSEG_NSTAT)[g] * inv_bn;
+        }
+      }
+    }
+    __syncthreads();
+    // the level's valid-sample count is complete only when all its samples sit in this round; with more pairs than
+    // slots the Dice coefficients are scaled by the pass at the end instead
+    const bool one_round = n_pairs <= SF_MAX_SLOTS;
+    if (live) {
+      float inv_nv = 1.f;
+      if (one_round) {
+        double nv = 0.0;
+        for (int bb = 0; bb < B; ++bb) nv += slot[L * B + bb][2];
+        inv_nv = nv > 0.0 ? (float)fast_div(1.0, nv) : 0.f;
+      }
+      float* dst = coef + o.c + (size_t)b * K * 3;
 #pragma unroll
-      for (int j = 0; j <= RHSEG_KERNEL_MAX_K; ++j) { row += rowv[j]; col += colv[j]; }
-      const long long fp = col - tp, fn = row - tp;
-      auto safe = [](float num, float den) { return num / (den == 0.f ? 1.f : den); };
-      const float tpf = (float)tp, fpf = (float)fp, fnf = (float)fn;
-      float* o = out + r_off[L];
-      o[0 * nc + c] = safe(2.0f * tpf, (2.0f * tpf + 1.0f * fnf) + fpf);
-      o[1 * nc + c] = safe(tpf, (float)(col + row - tp));
-      o[2 * nc + c] = safe(tpf, (float)(tp + fn));
-      o[3 * nc + c] = safe(tpf, (float)(tp + fp));
-      o[4 * nc + c] = safe(tpf, (float)(tp + fn));
+      for (int c = 0; c < RHSEG_KERNEL_MAX_K; ++c)
+        if (c < K) {
+          dst[c * 3 + 0] = cf[c * 3 + 0];
+          dst[c * 3 + 1] = cf[c * 3 + 1] * inv_nv;
+          dst[c * 3 + 2] = cf[c * 3 + 2] * inv_nv;
+        }
+    }
+    if (one_round) break;
+    // many pairs: accumulate this round's slots into per-level sums kept in the first slots' shadow (rare path)
+    __syncthreads();
+  }
+  const bool one_round = n_pairs <= SF_MAX_SLOTS;
+  __shared__ double lvl[RHSEG_MAX_LEVELS][4];
+  if (one_round) {
+    if (tid < nL) {  // fixed summation order over the samples: deterministic
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      for (int bb = 0; bb < B; ++bb) {
+        const double* sl = slot[tid * B + bb];
+        a0 += sl[0]; a1 += sl[1]; a2 += sl[2]; a3 += sl[3];
+      }
+      lvl[tid][0] = a0; lvl[tid][1] = a1; lvl[tid][2] = a2; lvl[tid][3] = a3;
+    }
+  } else {
+    // rare path (more than 256 (level, sample) pairs): recompute the level sums from the statistics, then scale the Dice
+    // coefficients in a second pass
+    if (tid < nL) {
+      const int K = lv.K[tid];
+      const StepOffsets o = step_offsets(lv, B, tid);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      float scratch[RHSEG_KERNEL_MAX_K * 3];
+      for (int bb = 0; bb < B; ++bb) {
+        const SampleLoss r = sample_loss(ws + o.w + (size_t)bb * K * RHSEG_NSTAT, weights + o.k, K, B, smooth, scratch);
+        a0 += r.ce;
+        if (r.dice_ok) { a1 += r.dice; a2 += 1.0; }
+        if (!r.ce_nan) a3 += 1.0;
+      }
+      lvl[tid][0] = a0; lvl[tid][1] = a1; lvl[tid][2] = a2; lvl[tid][3] = a3;
     }
   }
-  // (3) concurrently: consistency sums, thread <-> (level, group) in the middle of the block
-  if (tid >= 64 && tid < 64 + nL * RHSEG_MAX_K) {
-    const int L = (tid - 64) / RHSEG_MAX_K, g = (tid - 64) % RHSEG_MAX_K;
-    if (g < lv.G[L]) atomicAdd(&cons_sm[L], (ws + w_off[L] + (size_t)B * lv.K[L] * RHSEG_NSTAT)[g] * inv_bn);
-  }
   __syncthreads();
-  // dice coefficients carry 1/n_valid of their level
-  for (int L = 0; L < nL; ++L) {
-    const float inv_nv = acc[L][2] > 0.0 ? (float)fast_div(1.0, acc[L][2]) : 0.f;
-    float* cf = coef + c_off[L];
-    for (int i = tid; i < B * lv.K[L]; i += blockDim.x) {
-      cf[(size_t)i * 3 + 1] *= inv_nv;
-      cf[(size_t)i * 3 + 2] *= inv_nv;
+  if (!one_round) {
+    for (int L = 0; L < nL; ++L) {
+      const float inv_nv = lvl[L][2] > 0.0 ? (float)fast_div(1.0, lvl[L][2]) : 0.f;
+      float* cfl = coef + step_offsets(lv, B, L).c;
+      for (int i = tid; i < B * lv.K[L]; i += blockDim.x) {
+        cfl[(size_t)i * 3 + 1] *= inv_nv;
+        cfl[(size_t)i * 3 + 2] *= inv_nv;
+      }
+    }
+  }
+  if (tid < nL) {  // level tid's outputs
+    const int L = tid;
+    const float ce = (float)fast_div(lvl[L][0], (double)B);
+    const float dice = lvl[L][2] > 0.0 ? (float)fast_div(lvl[L][1], lvl[L][2]) : 0.f;
+    out[2 + 4 * L] = ce; out[3 + 4 * L] = dice; out[4 + 4 * L] = (float)lvl[L][2]; out[5 + 4 * L] = (float)lvl[L][3];
+    if (summary) {  // additive per-rank quantities for the data-parallel all-reduce (dist.py layout)
+      summary[2 + 4 * L] = lvl[L][0];
+      summary[3 + 4 * L] = lvl[L][1];
+      summary[4 + 4 * L] = lvl[L][2];
+      summary[5 + 4 * L] = lvl[L][3];
     }
   }
   if (tid == 0) {
@@ -298,32 +384,26 @@ step_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ we
     int cons_count = 0;
     float total = 0.f;
     for (int L = 0; L < nL; ++L) {
-      cons_total += cons_sm[L];  // sum over groups of mean |children - parent|
+      for (int g = 0; g < lv.G[L]; ++g) cons_total += cons_part[L][g];  // sum over groups of mean |children - parent|
       cons_count += lv.G[L];
-      const float ce = (float)fast_div(acc[L][0], (double)B);
-      const float dice = acc[L][2] > 0.0 ? (float)fast_div(acc[L][1], acc[L][2]) : 0.f;
-      out[2 + 4 * L] = ce; out[3 + 4 * L] = dice; out[4 + 4 * L] = (float)acc[L][2]; out[5 + 4 * L] = (float)acc[L][3];
+      const float ce = (float)fast_div(lvl[L][0], (double)B);
+      const float dice = lvl[L][2] > 0.0 ? (float)fast_div(lvl[L][1], lvl[L][2]) : 0.f;
       if ((level_mask >> L) & 1u) total += ce + dice;  // CE_L + Dice_L (0 when no sample is valid); curriculum: train.py:125-134
     }
     const float consf = cons_count > 0 ? (float)fast_div(cons_total, (double)cons_count) : 0.f;
     out[0] = total + consf;
     out[1] = consf;
-    if (summary) {  // additive per-rank quantities for the data-parallel all-reduce (dist.py layout)
+    if (summary) {
       summary[0] = (double)B;
       summary[1] = (double)consf * (double)B;
-      for (int L = 0; L < nL; ++L) {
-        summary[2 + 4 * L] = acc[L][0];
-        summary[3 + 4 * L] = acc[L][1];
-        summary[4 + 4 * L] = acc[L][2];
-        summary[5 + 4 * L] = acc[L][3];
-      }
     }
   }
   if (summary) {  // confusion counts as fp64 (exact below 2^53), level after level
     size_t s_off = 2 + 4 * (size_t)nL;
     for (int L = 0; L < nL; ++L) {
       const int K = lv.K[L], nc = lv.child[L] ? K + 1 : K;
-      const long long* conf = reinterpret_cast<const long long*>(ws + w_off[L] + (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K);
+      const StepOffsets o = step_offsets(lv, B, L);
+      const long long* conf = reinterpret_cast<const long long*>(ws + o.w + (size_t)B * K * RHSEG_NSTAT + RHSEG_MAX_K);
       for (int i = tid; i < nc * nc; i += blockDim.x) summary[s_off + i] = (double)conf[i];
       s_off += (size_t)nc * nc;
     }
