@@ -643,7 +643,9 @@ def run_ours(args, rank, world, local_rank):
     raw_call = native.call
 
     def counting_call(cname, *a):
-        counted["n"] += kernels_per_call(cname, upsampled)
+        # rhseg_head_conv_bwd_params: conv kernel + parameter-gradient kernel; a level without FiLM (film_w NULL) of a narrow
+        # donor (B*C*K <= 4096) is ONE launch (include/rhseg_b200.h)
+        counted["n"] += 1 if (cname == "rhseg_head_conv_bwd_params" and a[12] is None and a[3] * a[4] * a[5] <= 4096) else kernels_per_call(cname, upsampled)
         if timing_on["v"] and cname == "rhseg_head_conv_bwd_params":
             # the call launches the conv backward and the parameter-gradient kernel: issue the two launches it makes
             # separately (same kernels, same order, include/rhseg_b200.h) so that the event pair brackets the conv kernel only

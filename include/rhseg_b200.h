@@ -185,7 +185,9 @@ int rhseg_head_conv_bwd(const float* feats, const float* dz, const float* eff_w,
  * zero).  Two forms, same results: conv kernel + 12-CTA parameter kernel behind a programmatic dependent launch
  * (default, measured faster for C = 720), or the parameter gradients as the tail of the conv kernel's last CTA
  * (library built with -DRHSEG_WITH_PARAM_TAIL and RHSEG_PARAM_TAIL=1; compiled out by default because the tail costs
- * the conv kernel registers and, for 16-byte-aligned planes, its second CTA per SM).                              */
+ * the conv kernel registers and, for 16-byte-aligned planes, its second CTA per SM).  Exception: a level WITHOUT FiLM
+ * (film_w == NULL: d_head_w = sum_b S_b, d_head_b = sum_b s_b) of a narrow donor (B*C*K <= 4096) is always ONE launch,
+ * the sums being formed by the conv kernel's last CTA.                                                            */
 int rhseg_head_conv_bwd_params(const float* feats, const float* dz, const float* eff_w, int B, int C, int K,
                                int n_pix, float* dfeats, double* S, double* s, int flags, const float* head_w,
                                const float* film_w, const float* gamma_beta, const double* prev_psum,

@@ -453,11 +453,35 @@ conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, c
     advance();
   }
   if (cur_seg >= 0) flush();
+  // Level WITHOUT FiLM (level 0): its parameter gradients are plain sums over the batch, d_head_w = sum_b S_b and
+  // d_head_b = sum_b s_b.  The last CTA to finish forms them here (a few thousand L2 loads) instead of a second kernel
+  // at the very end of the step.  (The FiLM'd levels keep the separate 12-CTA kernel: their tail is the slower form.)
+  if (pt.ticket != nullptr && pt.film_w == nullptr) {
+    __shared__ int last_cta;
+    __threadfence();
+    consumer_sync(NCONS);
+    if (tid == 0) last_cta = (atomicAdd(pt.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    consumer_sync(NCONS);
+    if (last_cta) {
+      __threadfence();
+      for (int i = tid; i < K * C; i += NCONS) {
+        double a = 0.0;
+        for (int bb = 0; bb < pt.B; ++bb) a += __ldcg(S + (size_t)bb * K * C + i);  // accumulated by other CTAs: read at L2
+        pt.d_head_w[i] = (float)a;
+      }
+      if (tid < K) {
+        double a = 0.0;
+        for (int bb = 0; bb < pt.B; ++bb) a += __ldcg(s + bb * K + tid);
+        pt.d_head_b[tid] = (float)a;
+      }
+      if (tid == 0) *pt.ticket = 0u;  // ready for the next launch / graph replay
+    }
+  }
 #ifdef RHSEG_WITH_PARAM_TAIL
   // Compiled out by default: measured slower than the separate 12-CTA kernel (25 us against 8.6 us at C = 720), and the
   // call into the tail raised the 128-bit instance of this kernel from 96 to 128 registers, i.e. from two CTAs per SM
   // to one (UNet conv backward 0.81 -> 0.75 of the HBM peak).
-  if (pt.ticket != nullptr) {
+  if (pt.ticket != nullptr && pt.film_w != nullptr) {
     // last CTA done: S / s are complete -> parameter gradients (the ring is free: its memory holds the pool-gradient sums)
     __shared__ int is_last;
     __threadfence();
@@ -698,6 +722,13 @@ extern "C" int rhseg_head_conv_bwd_params(const float* feats, const float* dz, c
 #else
   use_tail = 0;
 #endif
+  // level 0 of a narrow donor: the batch sums are formed by the conv kernel's last CTA.  Measured: UNet (K*C*B = 1024 sums)
+  // 0.5507 vs 0.5538 ms per step with the separate kernel; HRNet-W48 (11520 sums through one CTA) 0.4207 vs 0.4166 -> kept
+  // for small heads only.
+  if (!film_w && (long)K * C * B <= 4096 && !getenv("RHSEG_NO_L0_TAIL")) {
+    ParamTail pt{ticket, head_w, nullptr, nullptr, nullptr, n_pix_out, B, 0, d_head_w, d_head_b, nullptr, nullptr, nullptr};
+    return conv_bwd_impl(feats, dz, eff_w, B, C, K, n_pix, dfeats, S, s, flags, stream, pt);
+  }
   if (!use_tail || (film_w && ((long)B * K_prev + 2L * B * C) * 8 > 60 * 1024)) {
     ParamTail none{};
     const int rc = conv_bwd_impl(feats, dz, eff_w, B, C, K, n_pix, dfeats, S, s, flags, stream, none);
