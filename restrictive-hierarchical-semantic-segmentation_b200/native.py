@@ -123,6 +123,9 @@ def stream_of(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+_current_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device  # the raw accessor: no lazy-init checks
+
+
 class _NoGuard:
     def __enter__(self):
         return None
@@ -138,7 +141,7 @@ def device_guard(t):
     """Context manager that makes the tensor's device current while kernels are launched for it (they launch on the
     device's current stream and size their grids for the current device).  Free when it already is."""
     idx = t.device.index
-    if idx is None or idx == torch.cuda.current_device():
+    if idx is None or idx == _current_device():
         return _NO_GUARD
     return torch.cuda.device(idx)
 
