@@ -201,10 +201,11 @@ __device__ __noinline__ void param_grads_tail(const ParamTail& pt, const double*
   }
 }
 
-// min-blocks 1 for the scalar-row K = 3 instance only (0 = unspecified): left alone, ptxas squeezes that instance to 96
-// registers (+ spills) for a second CTA per SM that the shared-memory ring rules out anyway -- 121 vs 112 us in the step.
+// min-blocks 1 (0 = unspecified) for the scalar-row instances other than K = 2 / K = 4: left alone, ptxas squeezes them to
+// 96 registers (+ spills) for a second CTA per SM that the shared-memory ring rules out anyway -- K = 3: 121 vs 112 us in
+// the step.  K = 4 (140 registers unprompted) and K = 2 measured no better with the hint and keep ptxas' own choice.
 template <int K, int VEC, int J, typename CFG>
-__global__ void __launch_bounds__(CFG::THREADS, ((VEC == 1 && K == 3) ? 1 : 0))
+__global__ void __launch_bounds__(CFG::THREADS, ((VEC == 1 && K != 2 && K != 4) ? 1 : 0))
 conv_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dz, const float* __restrict__ eff_w,
                 int C, int N, int n_tiles, int n_stages, long units_total, int a0, int w_shared, float* __restrict__ dfeats,
                 double* __restrict__ S, double* __restrict__ s, ParamTail pt) {
