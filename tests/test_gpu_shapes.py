@@ -169,3 +169,17 @@ def test_upsample_adjoint_kernels_agree_with_autograd(shape):
     again = torch.zeros(B, K, Hf, Wf, device=DEV)
     call("rhseg_upsample_adjoint", ptr(d), B, K, Hf, Wf, H, W, ptr(again), None, native.DZ_PREZEROED, st)
     assert torch.equal(again, outs["band"])
+
+
+@pytest.mark.parametrize("group", [1, 2, 3])
+def test_conv_backward_tile_groups(group):
+    """The conv backward walks (sample, tile group, channel stage, tile): small groups keep dz in L2 between channel
+    stages for large planes x batches (BASELINE configs[4]).  The group size is a per-process setting, so the check runs
+    in a worker process: planes of 4-5 tiles with a partial last group, 16-byte- and 4-byte-aligned."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, RHSEG_TUNE_BWD_GROUP=str(group))
+    r = subprocess.run([sys.executable, os.path.join(here, "conv_group_worker.py")], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "CONV_GROUP_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
