@@ -17,7 +17,6 @@ Models/, Metrics/, train.py staged by tools/stage_reference.py) on the host core
 """
 import argparse
 import json
-import math
 import os
 import statistics
 import subprocess
