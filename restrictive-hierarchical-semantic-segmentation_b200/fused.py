@@ -206,9 +206,12 @@ class _FusedStepFn(torch.autograd.Function):
                      native.DZ_PREZEROED, st)
             else:
                 dz = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
+                # nothing but the loss reaches the last active level's logits: the kernel instance without activation code
+                # (64 instead of 122 registers for a grouped K = 4 level) gives the same gradient
+                mode_bwd = native.ACT_ZEROS if (g_uniform is None and dp_pix is None) else mode
                 call("rhseg_head_dz_fullres_fused", ptr(logits[L]), t_ptr, t_bs, t_cs, c_ptr, g_ptrs[L][0], g_ptrs[L][1],
                      ptr(probs[L - 1]) if L > 0 else None, ptr(tables[L]), ptr(g_uniform), 1.0 / n_pix, ptr(dp_pix),
-                     pix_mask, B, K, K_prev, n_pix, mode, ptr(dz), ptr(dp_prev), st)
+                     pix_mask, B, K, K_prev, n_pix, mode_bwd, ptr(dz), ptr(dp_prev), st)
             d_feats[L], d_hw[L], d_hb[L], fw_g, fb_g, g_prev = level_weight_backward(
                 tree, L, ctx.dims, feats[L], dz, eff_ws[L], head_w[L], film_w[L - 1] if L > 0 else None, gbs[L],
                 psums[L - 1] if L > 0 else None, bufs[L], ctx.needs_input_grad[8 + L], st)
