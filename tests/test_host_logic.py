@@ -245,3 +245,21 @@ def test_batch_sharded_summary_exchange_gloo_world2():
     assert [r[1] for r in res] == [True, True], res
     # rank 0 holds samples 0-1 (sample 1 has no valid dice) -> 1 of 3 valid; rank 1 holds 2 of 3
     assert abs(res[0][2] - 2 * 1 / 3) < 1e-9 and abs(res[1][2] - 2 * 2 / 3) < 1e-9
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (CPU only): one JSON line, the same `config` object as our arm would print for the same
+    command line, the reference's own modules when they are staged (kind "reference"), the oracle port otherwise."""
+    import json
+    import subprocess
+    import bench
+    from oracle import ref_loader
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "flat7_620_b4",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mpixel/s" and line["higher_is_better"] is True
+    assert line["config"] == bench.config_of("flat7_620_b4", bench.WORKLOADS["flat7_620_b4"], 1)
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
