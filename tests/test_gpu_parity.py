@@ -381,3 +381,33 @@ def test_one_backward_per_loss_term_on_the_same_tensors():
     assert ce.grad_fn is di.grad_fn
     (ce + di).backward()
     close(logits.grad, z["dlogits"], what="dlogits, shared node")
+
+
+def test_fused_flat_step_matches_the_reference_fixture():
+    """rhseg_b200.FusedFlatStep (flat model, BASELINE.json configs[3]) on the reference-generated fixture: CE + Dice and
+    d(CE + Dice)/d logits against the reference's recorded values, confusion matrix and ratios against the oracle."""
+    import os
+    import numpy as np
+    from helpers import GOLDEN
+    import rhseg_b200
+    z = np.load(os.path.join(GOLDEN, "flat7.npz"))
+    logits = torch.from_numpy(z["logits"]).to(DEV).requires_grad_(True)
+    t = torch.from_numpy(z["target"]).float().to(DEV)
+    w = [float(v) for v in z["weights"]]
+    step = rhseg_b200.FusedFlatStep(7, w)
+    out = step(logits, t)
+    ref_total = float(z["ce"]) + float(z["dice"])
+    assert abs(out.loss.item() - ref_total) <= 1e-5 * abs(ref_total)
+    assert abs(out.level_ce[0].item() - float(z["ce"])) <= 1e-5 and abs(out.level_dice[0].item() - float(z["dice"])) <= 1e-5
+    out.loss.backward()
+    close(logits.grad, z["dlogits"], what="flat dlogits")
+    oh, et = O.predict_onehot_masked([logits.detach().cpu()], [t.cpu()])
+    want = O.level_confusion(oh[0], et[0], 7, False)
+    assert torch.equal(out.confusion[0].cpu(), want)
+    r = O.ratios_from_confusion(want)
+    for row, key in enumerate(("dice", "iou", "accuracy", "precision", "recall")):
+        assert torch.equal(out.ratios[0][row].cpu(), r[key]), key
+    # int8 targets and a channels-last target layout (what a one-hot permute produces) give the same result
+    out2 = step(logits.detach().requires_grad_(True), t.to(torch.int8))
+    out3 = step(logits.detach().requires_grad_(True), t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))
+    assert torch.equal(out2.scalars, out.scalars) and torch.equal(out3.scalars, out.scalars)
